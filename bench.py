@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — forward+backward seconds per dominant-eigenpair solve on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one solve of the TFIM ground state through the reference-shaped public API:
+    E0, psi0 = DominantSparseSymeig.apply(g, k, dim)         Lanczos, k vectors, full reorthogonalisation
+    dE0,     = torch.autograd.grad(E0, g)                    CG solve of (H - E0) x = b + adjoint contraction
+(examples/TFIM/E0.py:60-63 shape).  At 1 GPU the workload is TFIM N=24, k=200 — the largest BASELINE
+configuration whose fp64 Lanczos basis (26.8 GB) fits one GPU; at P GPUs the state vector is sharded by
+its top log2(P) spin bits with n_loc = 2^24 amplitudes per GPU (weak scaling: N = 24 + log2 P).
+
+Prints ONE JSON line (rank 0).  `value` = device-timed seconds per solve with g resident in HBM;
+`e2e` = the same through host buffers (g from pinned host memory, E0 / dE0 / psi0 copied back);
+`roofline` = the dominant kernel (re-orthogonalisation pass 2) timed live with CUDA events inside the
+timed region; `cpu_baseline` = the CPU oracle (restatement of the reference's PyTorch-CPU path) on a
+bounded sample.  `--impl reference` times only that CPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "tfim_fwd_bwd_seconds_per_solve"
+UNIT = "s/solve"
+SAMPLE_N, SAMPLE_K = 20, 100          # CPU sample: BASELINE config 2 shape (largest upstream fixture size)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spins", type=int, default=0, help="override N (default 24 + log2 gpus)")
+    ap.add_argument("--k", type=int, default=200)
+    ap.add_argument("--g", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-spins", type=int, default=SAMPLE_N)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.fh.close()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (port of the reference's PyTorch-CPU path) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+class _TimedCalls:
+    def __init__(self, fn):
+        self.fn, self.calls, self.seconds = fn, 0, 0.0
+
+    def __call__(self, v):
+        t = time.perf_counter()
+        out = self.fn(v)
+        self.seconds += time.perf_counter() - t
+        self.calls += 1
+        return out
+
+
+def cpu_sample_solve(model, k, seed):
+    """One E0 + dE0/dg solve with the oracle; returns timings split into operator / other work."""
+    from oracle import dsea_oracle as orc
+    H = _TimedCalls(model.H)
+    stats = {}
+    model.g = model.g.detach().clone().requires_grad_(True)
+    Dom, _ = orc.make_sparse_primitives(H, model.Hadjoint_to_gadjoint, orc.SeededDraws(seed), stats)
+    t0 = time.perf_counter()
+    E0, psi0 = Dom.apply(model.g, k, model.dim)
+    t1 = time.perf_counter()
+    mv_fwd, calls_fwd = H.seconds, H.calls
+    dE0, = torch.autograd.grad(E0, model.g)
+    t2 = time.perf_counter()
+    return {"fwd": t1 - t0, "bwd": t2 - t1, "mv_fwd": mv_fwd, "calls_fwd": calls_fwd,
+            "mv_bwd": H.seconds - mv_fwd, "calls_bwd": H.calls - calls_fwd, "cg_iters": stats["cg_iters"][-1],
+            "E0": E0.item(), "dE0": dE0.item()}
+
+
+def scale_cpu_sample(t, Ns, ks, Nw, kw):
+    """Extrapolates a sample solve (Ns spins, ks vectors) to the bench workload (Nw, kw) with the
+    reference's own cost model: the operator application moves (16N+24) 2^N bytes per
+    call; the re-orthogonalisation on the row-major (n, k) basis and the k x k Ritz GEMM scale as
+    2^N k^2; CG work scales with the operator (iteration count held at the sample's — an underestimate)."""
+    rn = 2.0 ** (Nw - Ns)
+    op = rn * (16 * Nw + 24) / (16 * Ns + 24)
+    fwd = t["mv_fwd"] * op * (kw / ks) + (t["fwd"] - t["mv_fwd"]) * rn * (kw / ks) ** 2
+    bwd = t["bwd"] * op
+    return fwd + bwd
+
+
+def run_cpu_arm(args, steps, warmup, Nw, kw):
+    from oracle import dsea_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ns, ks = args.cpu_sample_spins, SAMPLE_K
+    model = orc.TFIMOracle(Ns, torch.tensor([args.g], dtype=torch.float64))
+    model.H(torch.randn(model.dim, dtype=torch.float64))        # first application is 4-5x slower (page faults)
+    times, last = [], None
+    for i in range(warmup + steps):
+        if i < warmup and i >= 1:
+            continue                                             # one warm-up solve is enough on the CPU
+        last = cpu_sample_solve(model, ks, 100 + i)
+        if i >= warmup:
+            times.append(last)
+    med = lambda key: statistics.median(t[key] for t in times)
+    tmed = {key: med(key) for key in ("fwd", "bwd", "mv_fwd", "mv_bwd")}
+    measured = tmed["fwd"] + tmed["bwd"]
+    scaled = scale_cpu_sample(tmed, Ns, ks, Nw, kw)
+    sample = (f"oracle port of the reference PyTorch-CPU path: TFIM N={Ns}, k={ks}, g={args.g}, E0+dE0/dg, "
+              f"{len(times)} solve(s), measured {measured:.2f} s/solve (fwd {tmed['fwd']:.2f} s with "
+              f"{last['calls_fwd']} operator calls, bwd {tmed['bwd']:.2f} s with {last['calls_bwd']} calls, "
+              f"{last['cg_iters']} CG iterations); value = that scaled to N={Nw}, k={kw} by the reference's own "
+              f"byte model (operator ~ (16N+24)2^N per call, reorth/Ritz ~ 2^N k^2, CG iterations held fixed)")
+    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "measured_sample_seconds": measured}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    log2w = max(world, 1).bit_length() - 1
+    N = args.spins or (24 + log2w)
+    k = args.k
+    config = {"workload": f"tfim_N{N}_k{k}_E0_plus_dE0dg", "spins": N, "lanczos_vectors": k, "g": args.g,
+              "sharding": f"top{log2w}bits_x{world}" if world > 1 else "single_gpu",
+              "l2": "inputs_exceed_l2 (Lanczos basis %.1f GB per GPU)" % (k * 2.0 ** (N - log2w) * 8 / 1e9),
+              "cg": "as reference: eps=1e-7 absolute, random projected x0 (CG.py:25,121-122)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        cpu = run_cpu_arm(args, max(1, min(args.steps, 3)), min(args.warmup, 1), N, k)
+        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["measured_sample_seconds"] * 1e3,
+                "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_seconds": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import dominantsparseeigenad_b200 as dsea
+    rt = dsea.runtime.context()
+    dev = rt.device
+    model = dsea.TFIM(N)
+    dsea.symeig.setDominantSparseSymeig(model.H, model.Hadjoint_to_gadjoint)
+    solve = dsea.symeig.DominantSparseSymeig.apply
+    n_loc = model.n_loc
+
+    g_host = torch.tensor([args.g], dtype=torch.float64).pin_memory()
+    out_host = torch.empty(2, dtype=torch.float64).pin_memory()
+    psi_host = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    g_dev = g_host.to(dev)
+    results = {}
+
+    def step_device():
+        model.g = g_dev.detach().requires_grad_(True)
+        E0, psi0 = solve(model.g, k, model.dim, dev)
+        dE0, = torch.autograd.grad(E0, model.g)
+        results["E0"], results["dE0"] = E0, dE0
+
+    def step_e2e():
+        model.g = g_host.to(dev, non_blocking=True).requires_grad_(True)
+        E0, psi0 = solve(model.g, k, model.dim, dev)
+        dE0, = torch.autograd.grad(E0, model.g)
+        out_host[0:1].copy_(E0.detach().reshape(1), non_blocking=True)
+        out_host[1:2].copy_(dE0.detach().reshape(1), non_blocking=True)
+        psi_host.copy_(psi0.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    rt.profile_enable(True)
+    rt.profile_collect()
+    dsea.runtime.stats["cg_iters"].clear()
+    l0 = rt.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_total = timed(step_device, args.steps)
+    launches = rt.launch_count() - l0
+    prof = rt.profile_collect()
+    rt.profile_enable(False)
+    cg_iters = list(dsea.runtime.stats["cg_iters"])
+    clocks = clk.summary()
+    sec_per_solve = ms_total / 1e3 / args.steps
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_sec = ms_e2e / 1e3 / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    def kernel_line(name):
+        p = prof[name]
+        if p["launches"] == 0 or p["ms"] <= 0:
+            return None
+        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+        return {"achieved": gbs, "frac": gbs / peak, "launches_per_step": p["launches"] / args.steps,
+                "ms_per_step": p["ms"] / args.steps, "share_of_step": p["ms"] / ms_total,
+                "algorithmic_bytes_per_step": p["bytes"] / args.steps}
+
+    kernels = {nm: kernel_line(nm) for nm in prof if kernel_line(nm)}
+    dom = kernels.get("reorth_update")
+    roofline = None
+    if dom:
+        roofline = {"kernel": "reorth_update_kernel (r = u - Q c, pass 2 of full re-orthogonalisation)",
+                    "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "bytes_model": "8 n_loc (m + 2) per launch with m stored vectors (read Q[:, :m], read u, write r)",
+                    "share_of_step": dom["share_of_step"]}
+
+    line = {"metric": METRIC, "value": sec_per_solve, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 8,
+                    "d2h_bytes_per_step": 16 + 8 * n_loc},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "cg_iterations_per_solve": cg_iters, "E0": results["E0"].item(), "dE0": results["dE0"].item()}
+    try:
+        from oracle import dsea_oracle as orc
+        a = orc.tfim_analytic(N, args.g)
+        line["analytic_check"] = {"E0_rel_err": abs(line["E0"] - a[0]) / abs(a[0]),
+                                  "dE0_rel_err": abs(line["dE0"] - a[1]) / abs(a[1])}
+    except Exception as exc:  # the checker is optional for the measurement
+        line["analytic_check"] = {"error": repr(exc)}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_arm(args, 1, 1, N, k)
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,504 @@
+// api.cu — extern "C" boundary of libdsea.so (declared in include/dsea.h) and the host-side
+// orchestration of the device-resident Lanczos and CG loops.  No kernel lives here except the few
+// single-thread bookkeeping kernels that keep the loops free of host synchronisation.
+#include <stdarg.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dsea {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    int kind;
+    double bytes;
+};
+struct Profiler {
+    std::vector<ProfRec> recs;     // event pool, reused across collections
+    size_t used = 0;
+};
+
+int prof_begin(dsea_ctx* ctx, int kind, double bytes, cudaStream_t st) {
+    Profiler* p = ctx->prof;
+    if (!p) return -1;
+    if (p->used == p->recs.size()) {
+        ProfRec r;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+        p->recs.push_back(r);
+    }
+    ProfRec& r = p->recs[p->used];
+    r.kind = kind;
+    r.bytes = bytes;
+    cudaEventRecord(r.a, st);
+    return (int)p->used++;
+}
+
+void prof_end(dsea_ctx* ctx, int token, cudaStream_t st) {
+    if (token < 0 || !ctx->prof) return;
+    cudaEventRecord(ctx->prof->recs[token].b, st);
+}
+
+static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
+                    double* u, double* dot_out, double* work, cudaStream_t st) {
+    switch (op->kind) {
+        case DSEA_OP_TFIM:
+            DSEA_ARG(param != nullptr, "TFIM operator needs the device scalar g");
+            return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st);
+        case DSEA_OP_CSR:
+            return csr_apply(ctx, op, param, shift, v, u, dot_out, st);
+        case DSEA_OP_DENSE:
+            return dense_apply(ctx, op, shift, v, u, dot_out, st);
+    }
+    set_error("unknown operator kind %d", op->kind);
+    return DSEA_ERR_ARG;
+}
+
+// ---- Lanczos bookkeeping (single thread) -------------------------------------------------------
+__global__ void lanczos_reset_kernel(double* scal) {
+    scal[S_KEFF] = 0.0;
+    scal[S_BREAK] = 0.0;
+}
+
+// alpha[i] = c[i]; beta[i] = sqrt(beta2); flag breakdown (|r| == 0 or not finite) once.
+__global__ void lanczos_record_kernel(double* scal, const double* c, double* alpha, double* beta, int i, int has_beta) {
+    alpha[i] = c[i];
+    if (has_beta) {
+        const double b2 = scal[S_BETA2];
+        const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
+        beta[i] = b;
+        if (!(b > 0.0) || !isfinite(b)) {
+            if (scal[S_BREAK] == 0.0) {
+                scal[S_BREAK] = 1.0;
+                scal[S_KEFF] = (double)(i + 1);
+            }
+            scal[S_BETA2] = 0.0;      // makes the normalisation write a zero column
+        }
+    }
+}
+
+static int lanczos_start_impl(dsea_ctx* ctx, int64_t n, double* Q, cudaStream_t st) {
+    lanczos_reset_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    DSEA_TRY(dot(ctx, n, Q, Q, ctx->scal + S_BETA2, st));
+    return scale_by_inv_sqrt(ctx, n, Q, ctx->scal + S_BETA2, st);          // Lanczos.py:53
+}
+
+static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i, double* Q, const double* u,
+                             double* alpha, double* beta, cudaStream_t st) {
+    const int m = i + 1;
+    DSEA_TRY(reorth_dots(ctx, n, ldq, m, Q, u, ctx->cvec, st));                       // c = Q^T u; alpha_i = c_i
+    const bool more = (i < k - 1);
+    if (more) {
+        double* qnext = Q + (int64_t)m * ldq;
+        DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, u, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st));   // :61,66,69
+    }
+    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, ctx->cvec, alpha, beta, i, more ? 1 : 0);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    if (more) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));        // :70,75
+    return DSEA_OK;
+}
+
+static int lanczos_ritz_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int which, const double* Q,
+                             const double* alpha, const double* beta, double* evals, double* evec_min,
+                             double* evec_max, int64_t* info_host, cudaStream_t st) {
+    double* ymin = ctx->yvec;
+    double* ymax = ctx->yvec + kMaxK;
+    DSEA_TRY(tridiag_extreme(ctx, k, which, alpha, beta, ctx->scal + S_KEFF, evals, ymin, ymax, st));
+    if ((which == DSEA_MIN || which == DSEA_BOTH) && evec_min)
+        DSEA_TRY(reorth_update(ctx, n, ldq, k, Q, nullptr, ymin, 1.0, evec_min, nullptr, st));           // :99 (one column)
+    if ((which == DSEA_MAX || which == DSEA_BOTH) && evec_max)
+        DSEA_TRY(reorth_update(ctx, n, ldq, k, Q, nullptr, ymax, 1.0, evec_max, nullptr, st));
+    if (info_host) {
+        DSEA_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->scal + S_KEFF, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DSEA_CUDA(cudaStreamSynchronize(st));
+        const int64_t ke = (int64_t)ctx->pinned[0];
+        info_host[0] = ke > 0 ? ke : k;
+        info_host[1] = (int64_t)ctx->pinned[1];
+    }
+    return DSEA_OK;
+}
+
+static inline int64_t col_stride(int64_t n) { return (n + 15) & ~(int64_t)15; }
+
+}  // namespace dsea
+
+using namespace dsea;
+
+extern "C" {
+
+const char* dsea_last_error(void) { return g_err; }
+int dsea_version(void) { return 100; }
+
+int dsea_nccl_unique_id(void* id128_host) { return comm_unique_id(id128_host); }
+
+int dsea_ctx_create(int device, int rank, int world, const void* nccl_id_host, dsea_ctx** out) {
+    DSEA_ARG(out != nullptr, "out is NULL");
+    DSEA_ARG(world >= 1 && (world & (world - 1)) == 0 && world <= (1 << kMaxRemote), "world must be a power of two");
+    DSEA_ARG(rank >= 0 && rank < world, "rank out of range");
+    DSEA_CUDA(cudaSetDevice(device));
+    dsea_ctx* ctx = new (std::nothrow) dsea_ctx();
+    DSEA_ARG(ctx != nullptr, "out of host memory");
+    ctx->device = device;
+    ctx->rank = rank;
+    ctx->world = world;
+    while ((1 << ctx->log2world) < world) ++ctx->log2world;
+    cudaDeviceProp prop;
+    DSEA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("libdsea is built for sm_100a (B200) only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        delete ctx;
+        return DSEA_ERR_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    DSEA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    DSEA_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+    DSEA_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    DSEA_CUDA(cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming));
+    DSEA_CUDA(cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming));
+    DSEA_CUDA(cudaMalloc(&ctx->scal, S_COUNT * sizeof(double)));
+    DSEA_CUDA(cudaMemset(ctx->scal, 0, S_COUNT * sizeof(double)));
+    DSEA_CUDA(cudaMalloc(&ctx->partials, kPartialDoubles * sizeof(double)));
+    DSEA_CUDA(cudaMalloc(&ctx->cvec, kMaxK * sizeof(double)));
+    DSEA_CUDA(cudaMalloc(&ctx->yvec, 2 * kMaxK * sizeof(double)));
+    DSEA_CUDA(cudaMalloc(&ctx->tri_work, 10 * kMaxK * sizeof(double)));
+    DSEA_CUDA(cudaMallocHost(&ctx->pinned, 64 * sizeof(double)));
+    int s = comm_init(ctx, nccl_id_host);
+    if (s != DSEA_OK) return s;
+    *out = ctx;
+    return DSEA_OK;
+}
+
+int dsea_ctx_destroy(dsea_ctx* ctx) {
+    if (!ctx) return DSEA_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    comm_destroy(ctx);
+    cudaFree(ctx->scal);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->cvec);
+    cudaFree(ctx->yvec);
+    cudaFree(ctx->tri_work);
+    cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_ready);
+    cudaEventDestroy(ctx->ev_comm);
+    cudaEventDestroy(ctx->ev_poll[0]);
+    cudaEventDestroy(ctx->ev_poll[1]);
+    cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+    return DSEA_OK;
+}
+
+int dsea_ctx_rank(const dsea_ctx* ctx) { return ctx->rank; }
+int dsea_ctx_world(const dsea_ctx* ctx) { return ctx->world; }
+int64_t dsea_launch_count(const dsea_ctx* ctx) { return ctx->launches; }
+
+int dsea_profile_enable(dsea_ctx* ctx, int on) {
+    DSEA_ARG(ctx != nullptr, "NULL ctx");
+    if (on && !ctx->prof) ctx->prof = new (std::nothrow) Profiler();
+    if (on && ctx->prof) ctx->prof->used = 0;
+    if (!on && ctx->prof) {
+        for (auto& r : ctx->prof->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        delete ctx->prof;
+        ctx->prof = nullptr;
+    }
+    return DSEA_OK;
+}
+
+int dsea_profile_collect(dsea_ctx* ctx, int nkinds, double* ms_host, double* bytes_host, int64_t* count_host) {
+    DSEA_ARG(ctx && ms_host && bytes_host && count_host, "NULL argument");
+    for (int i = 0; i < nkinds; ++i) { ms_host[i] = 0.0; bytes_host[i] = 0.0; count_host[i] = 0; }
+    if (!ctx->prof) return DSEA_OK;
+    DSEA_CUDA(cudaDeviceSynchronize());
+    for (size_t i = 0; i < ctx->prof->used; ++i) {
+        const ProfRec& r = ctx->prof->recs[i];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        if (r.kind < nkinds) { ms_host[r.kind] += ms; bytes_host[r.kind] += r.bytes; count_host[r.kind] += 1; }
+    }
+    ctx->prof->used = 0;
+    return DSEA_OK;
+}
+
+int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
+    DSEA_ARG(ctx && key, "NULL argument");
+    if (!strcmp(key, "tfim_tile_bits")) ctx->tfim_tile_bits = (int)value;
+    else if (!strcmp(key, "tfim_run_bits")) ctx->tfim_run_bits = (int)value;
+    else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
+    else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (int)value;
+    else {
+        set_error("unknown option %s", key);
+        return DSEA_ERR_ARG;
+    }
+    return DSEA_OK;
+}
+
+// ---- operators ------------------------------------------------------------------------------------
+int dsea_op_tfim(dsea_ctx* ctx, int N, dsea_op** out) {
+    DSEA_ARG(ctx && out, "NULL argument");
+    DSEA_ARG(N >= 2 && N <= 40, "TFIM needs 2 <= N <= 40");
+    DSEA_ARG(N - ctx->log2world >= 1, "too few spins for this many ranks");
+    dsea_op* op = new (std::nothrow) dsea_op();
+    DSEA_ARG(op != nullptr, "out of host memory");
+    op->kind = DSEA_OP_TFIM;
+    op->ctx = ctx;
+    op->N = N;
+    op->L = N - ctx->log2world;
+    op->n_loc = (int64_t)1 << op->L;
+    *out = op;
+    return DSEA_OK;
+}
+
+int dsea_op_csr(dsea_ctx* ctx, int64_t n, int64_t nnz, const int64_t* rowptr, const int64_t* colidx,
+                const double* vals, dsea_op** out) {
+    DSEA_ARG(ctx && out && rowptr && (nnz == 0 || (colidx && vals)), "NULL argument");
+    DSEA_ARG(ctx->world == 1, "CSR operators are single-GPU");
+    dsea_op* op = new (std::nothrow) dsea_op();
+    DSEA_ARG(op != nullptr, "out of host memory");
+    op->kind = DSEA_OP_CSR;
+    op->ctx = ctx;
+    op->n_loc = n;
+    op->nnz = nnz;
+    op->rowptr = rowptr;
+    op->colidx = colidx;
+    op->vals = vals;
+    *out = op;
+    return DSEA_OK;
+}
+
+int dsea_op_dense(dsea_ctx* ctx, int64_t n, int64_t ld, const double* A, dsea_op** out) {
+    DSEA_ARG(ctx && out && A, "NULL argument");
+    DSEA_ARG(ctx->world == 1, "dense operators are single-GPU");
+    DSEA_ARG(ld >= n, "ld < n");
+    dsea_op* op = new (std::nothrow) dsea_op();
+    DSEA_ARG(op != nullptr, "out of host memory");
+    op->kind = DSEA_OP_DENSE;
+    op->ctx = ctx;
+    op->n_loc = n;
+    op->A = A;
+    op->ld = ld;
+    *out = op;
+    return DSEA_OK;
+}
+
+int dsea_op_destroy(dsea_op* op) {
+    delete op;
+    return DSEA_OK;
+}
+
+int64_t dsea_op_local_dim(const dsea_op* op) { return op->n_loc; }
+int64_t dsea_op_work_doubles(const dsea_op* op) {
+    return op->kind == DSEA_OP_TFIM ? (int64_t)op->ctx->log2world * op->n_loc : 0;
+}
+int64_t dsea_col_stride(int64_t n_loc) { return col_stride(n_loc); }
+
+int dsea_matvec(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
+                double* u, double* dot_out, double* work, void* stream) {
+    DSEA_ARG(ctx && op && v && u, "NULL argument");
+    DSEA_ARG(aligned16(v) && aligned16(u) && aligned16(work), "vectors must be 16-byte aligned");
+    DSEA_ARG(v != u, "in-place matvec is not supported");
+    return apply_op(ctx, op, param, shift, v, u, dot_out, work, (cudaStream_t)stream);
+}
+
+int dsea_tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, void* stream) {
+    DSEA_ARG(ctx && op && v && u && op->kind == DSEA_OP_TFIM, "dHdg needs a TFIM operator");
+    DSEA_ARG(aligned16(v) && aligned16(u) && aligned16(work) && v != u, "vectors must be distinct and 16-byte aligned");
+    return tfim_dHdg(ctx, op, v, u, work, (cudaStream_t)stream);
+}
+
+int dsea_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out, double* work,
+                 void* stream) {
+    DSEA_ARG(ctx && op && v1 && v2 && out, "NULL argument");
+    DSEA_ARG(aligned16(v1) && aligned16(v2) && aligned16(work), "vectors must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (op->kind) {
+        case DSEA_OP_TFIM:
+            return tfim_adjoint(ctx, op, v1, v2, out, work, st);
+        case DSEA_OP_CSR:
+            return hadamard(ctx, op->n_loc, v1, v2, out, st);
+        case DSEA_OP_DENSE:
+            return outer(ctx, op->n_loc, 1.0, v1, v2, out, st);
+    }
+    set_error("unknown operator kind %d", op->kind);
+    return DSEA_ERR_ARG;
+}
+
+// ---- Lanczos ----------------------------------------------------------------------------------------
+int64_t dsea_lanczos_work_doubles(const dsea_op* op) { return col_stride(op->n_loc) + dsea_op_work_doubles(op); }
+
+int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, int which, double* Q, double* work,
+                 double* alpha, double* beta, double* evals, double* evec_min, double* evec_max,
+                 int64_t* info_host, void* stream) {
+    DSEA_ARG(ctx && op && Q && work && alpha && beta && evals, "NULL argument");
+    DSEA_ARG(k >= 1 && k <= kMaxK, "k out of range");
+    DSEA_ARG(aligned16(Q) && aligned16(work) && aligned16(evec_min) && aligned16(evec_max), "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = op->n_loc, ldq = col_stride(n);
+    double* u = work;
+    double* opwork = work + ldq;
+    DSEA_TRY(lanczos_start_impl(ctx, n, Q, st));
+    for (int i = 0; i < k; ++i) {
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, nullptr, opwork, st));   // Lanczos.py:54,71
+        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st));
+    }
+    return lanczos_ritz_impl(ctx, n, ldq, k, which, Q, alpha, beta, evals, evec_min, evec_max, info_host, st);
+}
+
+int dsea_lanczos_start(dsea_ctx* ctx, int64_t n_loc, double* Q, void* stream) {
+    DSEA_ARG(ctx && Q && aligned16(Q), "bad Q");
+    return lanczos_start_impl(ctx, n_loc, Q, (cudaStream_t)stream);
+}
+
+int dsea_lanczos_step(dsea_ctx* ctx, int64_t n_loc, int k, int i, double* Q, const double* u, double* alpha,
+                      double* beta, void* stream) {
+    DSEA_ARG(ctx && Q && u && alpha && beta, "NULL argument");
+    DSEA_ARG(i >= 0 && i < k && k <= kMaxK, "step index out of range");
+    DSEA_ARG(aligned16(Q) && aligned16(u), "buffers must be 16-byte aligned");
+    return lanczos_step_impl(ctx, n_loc, col_stride(n_loc), k, i, Q, u, alpha, beta, (cudaStream_t)stream);
+}
+
+int dsea_lanczos_ritz(dsea_ctx* ctx, int64_t n_loc, int k, int which, const double* Q, const double* alpha,
+                      const double* beta, double* evals, double* evec_min, double* evec_max, int64_t* info_host,
+                      void* stream) {
+    DSEA_ARG(ctx && Q && alpha && beta && evals, "NULL argument");
+    DSEA_ARG(k >= 1 && k <= kMaxK, "k out of range");
+    DSEA_ARG(aligned16(Q) && aligned16(evec_min) && aligned16(evec_max), "buffers must be 16-byte aligned");
+    return lanczos_ritz_impl(ctx, n_loc, col_stride(n_loc), k, which, Q, alpha, beta, evals, evec_min, evec_max,
+                             info_host, (cudaStream_t)stream);
+}
+
+// ---- CG -----------------------------------------------------------------------------------------------
+int64_t dsea_cg_work_doubles(const dsea_op* op) { return 3 * col_stride(op->n_loc) + dsea_op_work_doubles(op); }
+
+static int cg_poll(dsea_ctx* ctx, int slot, cudaStream_t st) {
+    DSEA_CUDA(cudaMemcpyAsync(ctx->pinned + 8 * slot, ctx->scal + S_DONE, 3 * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));          // {done, iters, rnorm}
+    DSEA_CUDA(cudaEventRecord(ctx->ev_poll[slot], st));
+    return DSEA_OK;
+}
+
+int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* b, double* x,
+            double* work, double eps, int64_t maxit, int64_t* iters_host, void* stream) {
+    DSEA_ARG(ctx && op && b && x && work, "NULL argument");
+    DSEA_ARG(aligned16(b) && aligned16(x) && aligned16(work), "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = op->n_loc, ld = col_stride(n);
+    double* r = work;
+    double* d = work + ld;
+    double* Ad = work + 2 * ld;
+    double* opwork = work + 3 * ld;
+    if (maxit <= 0) maxit = n;                                                         // CG.py:32
+    DSEA_TRY(cg_setup(ctx, eps, maxit, st));
+    DSEA_TRY(apply_op(ctx, op, param, shift, x, Ad, nullptr, opwork, st));             // CG.py:27
+    DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st));
+    ctx->guard = ctx->scal + S_DONE;
+    int status = DSEA_OK;
+    int64_t issued = 0;
+    int slot = 0;
+    bool have_prev = false;
+    bool finished = false;
+    while (!finished) {
+        const int64_t chunk = ctx->cg_check_every;
+        for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
+            status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st);   // one matvec / iteration
+            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st);
+        }
+        if (status != DSEA_OK) break;
+        issued += chunk;
+        status = cg_poll(ctx, slot, st);
+        if (status != DSEA_OK) break;
+        if (have_prev) {      // look at the PREVIOUS chunk's flag while this chunk runs
+            cudaError_t e = cudaEventSynchronize(ctx->ev_poll[slot ^ 1]);
+            if (e != cudaSuccess) { set_error("CG poll failed: %s", cudaGetErrorString(e)); status = DSEA_ERR_CUDA; break; }
+            if (ctx->pinned[8 * (slot ^ 1)] != 0.0) finished = true;
+        }
+        have_prev = true;
+        slot ^= 1;
+        if (issued >= maxit) finished = true;
+    }
+    ctx->guard = nullptr;
+    if (status != DSEA_OK) return status;
+    DSEA_TRY(cg_poll(ctx, slot, st));
+    DSEA_CUDA(cudaStreamSynchronize(st));
+    const double done = ctx->pinned[8 * slot], iters = ctx->pinned[8 * slot + 1];
+    if (iters_host) *iters_host = (int64_t)iters;
+    (void)done;
+    return DSEA_OK;
+}
+
+int dsea_cg_init(dsea_ctx* ctx, int64_t n_loc, const double* b, const double* Ax, double* r, double* d,
+                 double* state_host, void* stream) {
+    DSEA_ARG(ctx && b && Ax && r && d, "NULL argument");
+    DSEA_ARG(aligned16(b) && aligned16(Ax) && aligned16(r) && aligned16(d), "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSEA_TRY(cg_setup(ctx, state_host ? state_host[0] : 1e-7, state_host ? (int64_t)state_host[1] : n_loc, st));
+    DSEA_TRY(cg_init(ctx, n_loc, b, Ax, r, d, st));
+    if (state_host) {
+        DSEA_TRY(cg_poll(ctx, 0, st));
+        DSEA_CUDA(cudaStreamSynchronize(st));
+        state_host[0] = ctx->pinned[2];
+        state_host[1] = ctx->pinned[1];
+        state_host[2] = ctx->pinned[0];
+    }
+    return DSEA_OK;
+}
+
+int dsea_cg_update(dsea_ctx* ctx, int64_t n_loc, double* x, double* r, double* d, const double* Ad,
+                   double* state_host, void* stream) {
+    DSEA_ARG(ctx && x && r && d && Ad, "NULL argument");
+    DSEA_ARG(aligned16(x) && aligned16(r) && aligned16(d) && aligned16(Ad), "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSEA_TRY(dot(ctx, n_loc, d, Ad, ctx->scal + S_DAD, st));
+    DSEA_TRY(cg_iterate(ctx, n_loc, x, r, d, Ad, st));
+    if (state_host) {
+        DSEA_TRY(cg_poll(ctx, 0, st));
+        DSEA_CUDA(cudaStreamSynchronize(st));
+        state_host[0] = ctx->pinned[2];
+        state_host[1] = ctx->pinned[1];
+        state_host[2] = ctx->pinned[0];
+    }
+    return DSEA_OK;
+}
+
+// ---- level 1 ----------------------------------------------------------------------------------------------
+int dsea_dot(dsea_ctx* ctx, int64_t n_loc, const double* a, const double* b, double* out, void* stream) {
+    DSEA_ARG(ctx && a && b && out && aligned16(a) && aligned16(b), "bad argument");
+    return dot(ctx, n_loc, a, b, out, (cudaStream_t)stream);
+}
+
+int dsea_project(dsea_ctx* ctx, int64_t n_loc, const double* psi, const double* b, double* out, void* stream) {
+    DSEA_ARG(ctx && psi && b && out && aligned16(psi) && aligned16(b) && aligned16(out), "bad argument");
+    return project(ctx, n_loc, psi, b, out, (cudaStream_t)stream);
+}
+
+int dsea_axpby(dsea_ctx* ctx, int64_t n_loc, const double* a, const double* x, const double* b, double* y,
+               void* stream) {
+    DSEA_ARG(ctx && x && y && aligned16(x) && aligned16(y), "bad argument");
+    return axpby(ctx, n_loc, a, x, b, y, (cudaStream_t)stream);
+}
+
+int dsea_outer(dsea_ctx* ctx, int64_t n, double scale, const double* a, const double* b, double* out, void* stream) {
+    DSEA_ARG(ctx && a && b && out, "bad argument");
+    return outer(ctx, n, scale, a, b, out, (cudaStream_t)stream);
+}
+
+int dsea_randn(dsea_ctx* ctx, int64_t n_loc, uint64_t seed, uint64_t stream_id, double* out, void* stream) {
+    DSEA_ARG(ctx && out, "bad argument");
+    return randn(ctx, n_loc, seed, stream_id, (uint64_t)ctx->rank * (uint64_t)n_loc, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// common.cuh — shared declarations for libdsea (sm_100a).  Internal; the public ABI is include/dsea.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dsea.h"
+
+namespace dsea {
+
+void set_error(const char* fmt, ...);
+
+#define DSEA_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            dsea::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                            cudaGetErrorString(_e));                                            \
+            return DSEA_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+
+#define DSEA_TRY(expr)               \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != DSEA_OK) return _s; \
+    } while (0)
+
+#define DSEA_ARG(cond, msg)                                                  \
+    do {                                                                     \
+        if (!(cond)) {                                                       \
+            dsea::set_error("%s:%d invalid argument: %s", __FILE__, __LINE__, msg); \
+            return DSEA_ERR_ARG;                                             \
+        }                                                                    \
+    } while (0)
+
+constexpr int kMaxRemote = 8;        // log2(max world) remote (top) spin bits
+constexpr int kMaxSweeps = 8;
+constexpr int kMaxPartialBlocks = 4096;   // upper bound on CTAs writing reduction partials
+constexpr int kMaxK = 2048;               // max Lanczos vectors
+constexpr int64_t kPartialDoubles = 4 << 20;   // 32 MB of per-CTA partial sums (>= kMaxPartialBlocks * 1024)
+
+// ---- device scalars kept in ctx->scal (all double) -------------------------------------------
+enum ScalarSlot {
+    S_DOT = 0,        // generic dot result
+    S_BETA2,          // |r|^2 of the current Lanczos step
+    S_INVBETA,        // 1 / beta
+    S_RR,             // CG: r.r (current)
+    S_RR_NEW,         // CG: r.r (next)
+    S_DAD,            // CG: d.Ad
+    S_ALPHA,          // CG: step length
+    S_BETA,           // CG: direction update coefficient
+    S_DONE,           // CG: 1.0 when converged / finished (kernels become no-ops)
+    S_ITERS,          // CG: iterations performed
+    S_RNORM,          // CG: |r|
+    S_KEFF,           // Lanczos: effective k (breakdown truncation), as double
+    S_BREAK,          // Lanczos: 1.0 if breakdown occurred
+    S_EPS,            // CG: tolerance
+    S_MAXIT,          // CG: iteration cap
+    S_TMP0,
+    S_TMP1,
+    S_COUNT = 32
+};
+
+struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
+struct Profiler;  // optional per-kernel CUDA-event timing (api.cu)
+
+enum ProfKind { PK_MATVEC = 0, PK_REORTH_DOTS, PK_REORTH_UPDATE, PK_RITZ, PK_CG_UPDATE, PK_NORMALISE, PK_TRIDIAG,
+                PK_ADJOINT, PK_COUNT };
+
+}  // namespace dsea
+
+struct dsea_ctx {
+    int device = 0;
+    int rank = 0;
+    int world = 1;
+    int log2world = 0;
+    int num_sms = 148;
+    void* nccl_comm = nullptr;          // ncclComm_t
+    dsea::NcclApi* nccl = nullptr;
+    cudaStream_t comm_stream = nullptr; // exchanges of top-bit shards run here, overlapped with the local sweep
+    cudaEvent_t ev_ready = nullptr, ev_comm = nullptr, ev_poll[2] = {nullptr, nullptr};
+    double* scal = nullptr;             // S_COUNT device scalars
+    double* partials = nullptr;         // kPartialDoubles doubles of per-CTA reduction partials
+    double* cvec = nullptr;             // kMaxK doubles: reorth coefficients / Ritz coefficients
+    double* yvec = nullptr;             // 2*kMaxK doubles: tridiagonal eigenvectors (min, max)
+    double* tri_work = nullptr;         // tridiagonal solver scratch
+    double* pinned = nullptr;           // small pinned host buffer for polling
+    unsigned int* counters = nullptr;   // device counters (last-block patterns)
+    int64_t launches = 0;
+    const double* guard = nullptr;      // device flag consulted by operator kernels (set during CG)
+    dsea::Profiler* prof = nullptr;     // non-null while per-kernel timing is enabled
+    // options
+    int tfim_tile_bits = 13;
+    int tfim_run_bits = 0;              // 0 = auto
+    int cg_check_every = 16;
+    int reorth_ctas_per_sm = 4;
+};
+
+struct dsea_op {
+    int kind = 0;
+    dsea_ctx* ctx = nullptr;
+    int64_t n_loc = 0;
+    // TFIM
+    int N = 0;
+    int L = 0;                  // local bits = N - log2(world)
+    // CSR
+    int64_t nnz = 0;
+    const int64_t* rowptr = nullptr;
+    const int64_t* colidx = nullptr;
+    const double* vals = nullptr;
+    // dense
+    const double* A = nullptr;
+    int64_t ld = 0;
+};
+
+namespace dsea {
+
+// ---- internal kernels' host launchers (each returns a DSEA status) ----------------------------
+// tfim.cu
+int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
+               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st);
+int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st);
+int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
+                 double* work, cudaStream_t st);
+// spmv.cu
+int csr_apply(dsea_ctx* ctx, const dsea_op* op, const double* pdiag, const double* shift, const double* v,
+              double* u, double* dot_out, cudaStream_t st);
+int dense_apply(dsea_ctx* ctx, const dsea_op* op, const double* shift, const double* v, double* u,
+                double* dot_out, cudaStream_t st);
+int hadamard(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st);
+int outer(dsea_ctx* ctx, int64_t n, double scale, const double* a, const double* b, double* out, cudaStream_t st);
+// reorth.cu
+int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u, double* c_out,
+                cudaStream_t st);   // c_out[0..ncols) = Q^T u  (allreduced)
+int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u,
+                  const double* c, double sign, double* r_out, double* norm2_out,
+                  cudaStream_t st);   // r = u + sign * Q c  (u may be NULL)
+int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, cudaStream_t st);
+// blas1.cu
+int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st);
+int axpby(dsea_ctx* ctx, int64_t n, const double* a, const double* x, const double* b, double* y, cudaStream_t st);
+int project(dsea_ctx* ctx, int64_t n, const double* psi, const double* b, double* out, cudaStream_t st);
+int randn(dsea_ctx* ctx, int64_t n, uint64_t seed, uint64_t sid, uint64_t offset, double* out, cudaStream_t st);
+int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st);
+// tridiag.cu
+int tridiag_extreme(dsea_ctx* ctx, int k, int which, const double* alpha, const double* beta, const double* keff,
+                    double* evals, double* y_min, double* y_max, cudaStream_t st);
+// cg.cu
+int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st);
+int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st);
+int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st);
+// comm.cu
+int comm_init(dsea_ctx* ctx, const void* id);
+int comm_destroy(dsea_ctx* ctx);
+int comm_unique_id(void* id128);
+int allreduce_sum(dsea_ctx* ctx, double* buf, int64_t count, cudaStream_t st);
+int exchange_shards(dsea_ctx* ctx, const double* send, double* recv_base, int64_t n_loc, cudaStream_t st);
+
+inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
+
+// Per-kernel timing with CUDA events on the launching stream (no-ops unless dsea_profile_enable()).
+int prof_begin(dsea_ctx* ctx, int kind, double algorithmic_bytes, cudaStream_t st);
+void prof_end(dsea_ctx* ctx, int token, cudaStream_t st);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` must hold >= 32 doubles.  Fixed order => deterministic.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();            // protect `red` from a previous use
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void stg2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+
+// streaming (evict-first) 16-byte load for data touched once per kernel
+__device__ __forceinline__ double2 ldg2_stream(const double* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace dsea

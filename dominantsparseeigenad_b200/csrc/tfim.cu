@@ -1,0 +1,271 @@
+// tfim.cu — matrix-free transverse-field Ising operator on the 2^N spin basis (K1, K6).
+//
+//   u[s] = diag(s) v[s] - g * sum_{i<N} v[s ^ (1<<i)]  (- shift * v[s])
+//   diag(s) = -(N - 2 popc(s ^ rotl_N(s)))             (bit-exact restatement of TFIM.py:39-46)
+//   flip index s ^ (1<<i)                              (TFIM.py:48-51)
+//
+// No index table exists: the reference's (2^N, N) int64 table (60 GB at N=28) is replaced by bit
+// arithmetic on the global index (rank << L) | s_loc.
+//
+// Memory plan.  A CTA stages a TILE of 2^T doubles in shared memory and serves every flip whose
+// bit lies inside the tile from there, so each vector element is read from HBM once per SWEEP:
+//   sweep 0 : tile = 2^T contiguous doubles            -> handles spin bits [0, T)
+//   sweep j : tile = 2^c contiguous x 2^h strided runs -> handles h spin bits starting at `hshift`
+//             (run stride 2^hshift doubles; c >= 2 keeps every global access a full 32 B sector,
+//             c >= 4 a full 128 B line)
+//   top log2(world) bits : whole-shard exchange with rank ^ (1<<j) over NCCL on a side stream,
+//             overlapped with the local sweeps and consumed by the last sweep.
+// HBM bytes per element: 16 (first sweep: read v, write u) + 24 per extra sweep (read v, read u,
+// write u) + 8 per remote bit.  The dot-product epilogue (v.u for CG, or w.u) rides on the last sweep.
+#include "common.cuh"
+
+namespace dsea {
+
+struct Sweep {
+    int T;        // tile bits
+    int c;        // contiguous low bits of the tile
+    int hshift;   // global bit position of tile bit c
+    int b0;       // first tile bit this sweep is responsible for
+};
+
+struct SweepParams {
+    const double* v;
+    const double* uin;
+    double* uout;
+    const double* w;        // dot partner (may alias v); nullptr = no dot
+    const double* g;
+    const double* shift;
+    const double* recv;     // nrecv buffers of n_loc doubles each
+    const double* guard;    // if non-null and != 0 the kernel is a no-op (CG converged)
+    double* partials;
+    uint64_t rank_off;      // rank << L
+    uint64_t n_loc;
+    uint64_t ntiles;
+    int nrecv;
+    int N, T, c, hshift, b0;
+    int no_diag;            // 1: drop the diagonal (u = -g * flip sum), used for dH/dg
+};
+
+__device__ __forceinline__ double tfim_diag_dev(uint64_t s, int N, uint64_t mask) {
+    const uint64_t rot = ((s << 1) | (s >> (N - 1))) & mask;
+    return -(double)(N - 2 * __popcll(s ^ rot));
+}
+
+constexpr int kSweepThreads = 512;
+enum { MODE_FIRST = 0, MODE_ACCUM = 1, MODE_ADJ = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) double tile[];
+    __shared__ double red[32];
+    if (p.guard && *p.guard != 0.0) return;
+    const int T = p.T, c = p.c;
+    const uint32_t cmask = (1u << c) - 1u;
+    const int half = 1 << (T - 1);
+    const int midbits = p.hshift - c;
+    const uint64_t nmask = (p.N >= 64) ? ~0ull : ((1ull << p.N) - 1ull);
+    const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
+    const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
+    double part = 0.0;
+
+    for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const uint64_t t_mid = t & ((1ull << midbits) - 1ull), t_up = t >> midbits;
+        const uint64_t base = (t_mid << c) | (t_up << (p.hshift + T - c));
+        // ---- stage the tile (coalesced 16 B loads; runs of 2^c doubles) ----
+#pragma unroll 4
+        for (int e2 = threadIdx.x; e2 < half; e2 += kSweepThreads) {
+            const uint32_t e = 2u * e2;
+            const uint64_t gi = base | (e & cmask) | ((uint64_t)(e >> c) << p.hshift);
+            *reinterpret_cast<double2*>(&tile[e]) = ldg2(p.v + gi);
+        }
+        __syncthreads();
+        // ---- neighbour sums from shared memory ----
+#pragma unroll 2
+        for (int e2 = threadIdx.x; e2 < half; e2 += kSweepThreads) {
+            const uint32_t e = 2u * e2;
+            const uint64_t gi = base | (e & cmask) | ((uint64_t)(e >> c) << p.hshift);
+            const double2 x = *reinterpret_cast<const double2*>(&tile[e]);
+            double a0 = 0.0, a1 = 0.0;
+            int b = p.b0;
+            if (b == 0) { a0 = x.y; a1 = x.x; b = 1; }        // bit 0: the pair partner
+            for (; b < T; ++b) {
+                const double2 y = *reinterpret_cast<const double2*>(&tile[e ^ (1u << b)]);
+                a0 += y.x;
+                a1 += y.y;
+            }
+            for (int j = 0; j < p.nrecv; ++j) {                 // top (remote) spin bits
+                const double2 y = ldg2(p.recv + (uint64_t)j * p.n_loc + gi);
+                a0 += y.x;
+                a1 += y.y;
+            }
+            if (MODE == MODE_ADJ) {
+                const double2 wv = ldg2(p.w + gi);
+                part -= wv.x * a0 + wv.y * a1;
+            } else {
+                double2 o;
+                if (MODE == MODE_FIRST) {
+                    const uint64_t s = p.rank_off | gi;
+                    const double d0 = p.no_diag ? 0.0 : tfim_diag_dev(s, p.N, nmask);
+                    const double d1 = p.no_diag ? 0.0 : tfim_diag_dev(s | 1ull, p.N, nmask);
+                    o.x = (d0 - shift) * x.x - g * a0;
+                    o.y = (d1 - shift) * x.y - g * a1;
+                } else {
+                    const double2 ui = ldg2(p.uin + gi);
+                    o.x = ui.x - g * a0;
+                    o.y = ui.y - g * a1;
+                }
+                stg2(p.uout + gi, o);
+                if (p.w) {
+                    const double2 wv = (p.w == p.v) ? x : ldg2(p.w + gi);
+                    part += wv.x * o.x + wv.y * o.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.partials) {
+        const double tot = block_sum(part, red);
+        if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
+    }
+}
+
+// Sweep schedule for L local bits with tiles of at most Tmax bits.
+static int plan_sweeps(int L, int Tmax, int run_bits, Sweep* out) {
+    int n = 0;
+    const int T1 = L < Tmax ? L : Tmax;
+    out[n++] = Sweep{T1, T1, T1, 0};
+    int rem = L - T1, pos = T1;
+    if (rem > 0) {
+        int c = run_bits;
+        if (c <= 0) {
+            // fewest sweeps subject to c >= 2 (32 B sectors); then the longest runs that keep that count
+            const int nmin = (rem + (Tmax - 2) - 1) / (Tmax - 2);
+            c = 2;
+            for (int cc = 3; cc <= 8 && cc < Tmax; ++cc)
+                if ((rem + (Tmax - cc) - 1) / (Tmax - cc) == nmin) c = cc;
+        }
+        if (c > T1) c = T1;
+        if (c < 1) c = 1;
+        int nsw = (rem + (Tmax - c) - 1) / (Tmax - c);
+        while (rem > 0 && n < kMaxSweeps) {
+            const int h = (rem + nsw - 1) / nsw;
+            out[n++] = Sweep{c + h, c, pos, c};
+            pos += h;
+            rem -= h;
+            --nsw;
+        }
+        if (rem > 0) return -1;
+    }
+    return n;
+}
+
+template <int MODE>
+static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream_t st) {
+    const size_t smem = sizeof(double) << p.T;
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[MODE]) {
+        DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(double) << 14)));
+        attr_done[MODE] = true;
+    }
+    tfim_sweep_kernel<MODE><<<grid, kSweepThreads, smem, st>>>(p);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    return DSEA_OK;
+}
+
+// Shared driver: mode_adj=false -> u = H v (- shift v), optional dot with `dotw`;
+//                mode_adj=true  -> out = -sum_s w[s] * sum_i v[s^(1<<i)].
+static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const double* g, const double* shift,
+                    const double* v, double* u, const double* w, double* dot_out, double* work,
+                    cudaStream_t st) {
+    Sweep sw[kMaxSweeps];
+    const int L = op->L;
+    int Tmax = ctx->tfim_tile_bits;
+    if (Tmax > 14) Tmax = 14;
+    if (Tmax < 3) Tmax = 3;
+    const int ns = plan_sweeps(L, Tmax, ctx->tfim_run_bits, sw);
+    DSEA_ARG(ns > 0, "TFIM sweep plan failed");
+    const int nrecv = ctx->log2world;
+    DSEA_ARG(nrecv == 0 || work != nullptr, "sharded TFIM matvec needs a work buffer");
+
+    if (nrecv > 0) {   // top-bit shards travel on the side stream while the local sweeps run
+        DSEA_CUDA(cudaEventRecord(ctx->ev_ready, st));
+        DSEA_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
+        DSEA_TRY(exchange_shards(ctx, v, work, op->n_loc, ctx->comm_stream));
+        DSEA_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+    }
+    const bool want_dot = mode_adj || (dot_out != nullptr);
+    int total_partials = 0;
+    const int tok = prof_begin(ctx, mode_adj ? PK_ADJOINT : PK_MATVEC, 16.0 * (double)op->n_loc, st);
+    for (int j = 0; j < ns; ++j) {
+        const bool last = (j == ns - 1);
+        SweepParams p;
+        p.v = v;
+        p.uin = u;
+        p.uout = u;
+        p.g = g;
+        p.shift = shift;
+        p.recv = work;
+        p.guard = ctx->guard;
+        p.no_diag = (!mode_adj && g == nullptr) ? 1 : 0;
+        p.nrecv = last ? nrecv : 0;
+        p.rank_off = (uint64_t)ctx->rank << L;
+        p.n_loc = (uint64_t)op->n_loc;
+        p.N = op->N;
+        p.T = sw[j].T;
+        p.c = sw[j].c;
+        p.hshift = sw[j].hshift;
+        p.b0 = sw[j].b0;
+        p.ntiles = 1ull << (L - sw[j].T);
+        int grid = (int)(p.ntiles < 2048 ? p.ntiles : 2048);
+        if (last && nrecv > 0) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
+        if (mode_adj) {
+            p.w = w;
+            p.partials = ctx->partials + total_partials;   // every sweep contributes partial sums
+            total_partials += grid;
+            DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, st));
+        } else {
+            p.w = (last && want_dot) ? w : nullptr;
+            p.partials = (last && want_dot) ? ctx->partials : nullptr;
+            if (last && want_dot) total_partials = grid;
+            if (j == 0) DSEA_TRY(launch_sweep<MODE_FIRST>(ctx, p, grid, st));
+            else DSEA_TRY(launch_sweep<MODE_ACCUM>(ctx, p, grid, st));
+        }
+    }
+    prof_end(ctx, tok, st);
+    if (want_dot) {
+        DSEA_TRY(finalize_partials(ctx, total_partials, 1, dot_out, st));
+        DSEA_TRY(allreduce_sum(ctx, dot_out, 1, st));
+    }
+    return DSEA_OK;
+}
+
+int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
+               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st) {
+    return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st);
+}
+
+// u = (dH/dg) v: the same sweeps with g = 1 and the diagonal dropped (g == nullptr selects this).
+int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st) {
+    return tfim_run(ctx, op, false, nullptr, nullptr, v, u, v, nullptr, work, st);
+}
+
+int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
+                 double* work, cudaStream_t st) {
+    return tfim_run(ctx, op, true, nullptr, nullptr, v2, nullptr, v1, out, work, st);
+}
+
+}  // namespace dsea
+
+extern "C" int64_t dsea_tfim_flip_index(int N, int64_t s, int i) {
+    (void)N;
+    return s ^ ((int64_t)1 << i);
+}
+
+extern "C" double dsea_tfim_diag(int N, int64_t s) {
+    const uint64_t mask = (N >= 64) ? ~0ull : ((1ull << N) - 1ull);
+    const uint64_t us = (uint64_t)s;
+    const uint64_t rot = ((us << 1) | (us >> (N - 1))) & mask;
+    return -(double)(N - 2 * __builtin_popcountll(us ^ rot));
+}

@@ -1,0 +1,148 @@
+"""Process-level runtime: the libdsea context (one per process = one per GPU), pointer/stream
+plumbing between torch tensors and the C ABI, and the start-vector source.
+
+torch is used here only for device memory, streams and (when launched under torchrun) for the
+rendezvous that distributes the ncclUniqueId.  No compute goes through torch on the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+_ctx = None
+_start_vector_hook: Optional[Callable[[int, str], Optional[torch.Tensor]]] = None
+_draw_counter = 0
+stats = {"cg_iters": [], "lanczos_calls": 0, "cg_calls": 0}
+
+
+class Context:
+    """Owns a dsea_ctx*.  rank/world follow torch.distributed when it is initialised."""
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise _lib.DseaError("dominantsparseeigenad_b200 needs a CUDA device (B200, sm_100a); "
+                                 "there is no CPU fallback.")
+        self.lib = _lib.load()
+        rank, world = 0, 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        if world > 1:
+            self.device_index = int(os.environ.get("LOCAL_RANK", rank % max(torch.cuda.device_count(), 1)))
+        else:
+            self.device_index = torch.cuda.current_device()
+        torch.cuda.set_device(self.device_index)
+        self.device = torch.device("cuda", self.device_index)
+        id_buf = None
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                raw = (C.c_ubyte * 128)()
+                _lib.check(self.lib.dsea_nccl_unique_id(raw))
+                idt = torch.tensor(list(raw), dtype=torch.uint8)
+            backend = torch.distributed.get_backend()
+            if backend == "nccl":
+                idt = idt.to(self.device)
+            torch.distributed.broadcast(idt, src=0)
+            id_buf = (C.c_ubyte * 128)(*idt.cpu().tolist())
+        handle = C.c_void_p()
+        _lib.check(self.lib.dsea_ctx_create(self.device_index, rank, world, id_buf, C.byref(handle)))
+        self.handle = handle
+        self.rank, self.world = rank, world
+        self.log2world = world.bit_length() - 1
+
+    def set_option(self, key: str, value: int) -> None:
+        _lib.check(self.lib.dsea_ctx_set_option(self.handle, key.encode(), int(value)))
+
+    def launch_count(self) -> int:
+        return int(self.lib.dsea_launch_count(self.handle))
+
+    PROFILE_KINDS = ("matvec", "reorth_dots", "reorth_update", "ritz", "cg_update", "normalise", "tridiag",
+                     "adjoint")
+
+    def profile_enable(self, on: bool = True) -> None:
+        _lib.check(self.lib.dsea_profile_enable(self.handle, 1 if on else 0))
+
+    def profile_collect(self) -> dict:
+        """{kind: {"ms", "bytes", "launches"}} accumulated since the previous collect (synchronises)."""
+        n = len(self.PROFILE_KINDS)
+        ms, by, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.dsea_profile_collect(self.handle, n, ms, by, cnt))
+        return {k: {"ms": ms[i], "bytes": by[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_KINDS)}
+
+    def col_stride(self, n: int) -> int:
+        return int(self.lib.dsea_col_stride(n))
+
+
+def context() -> Context:
+    global _ctx
+    if _ctx is None:
+        _ctx = Context()
+        for key, env in (("tfim_tile_bits", "DSEA_TFIM_TILE_BITS"), ("tfim_run_bits", "DSEA_TFIM_RUN_BITS"),
+                         ("cg_check_every", "DSEA_CG_CHECK_EVERY"), ("reorth_ctas_per_sm", "DSEA_REORTH_CTAS")):
+            if os.environ.get(env):
+                _ctx.set_option(key, int(os.environ[env]))
+    return _ctx
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous fp64 CUDA tensor (None passes NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == F64 and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    return t.data_ptr()
+
+
+def dev_vec(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """fp64, contiguous, 16-byte aligned copy-if-needed of `t` on `device` (detached)."""
+    t = t.detach()
+    if t.device != device or t.dtype != F64:
+        t = t.to(device=device, dtype=F64)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def empty(n: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(int(n), dtype=F64, device=device)
+
+
+# ---- start vectors -------------------------------------------------------------------------------
+def set_start_vector_hook(fn: Optional[Callable[[int, str], Optional[torch.Tensor]]]) -> None:
+    """Tests use this to inject q0 / x0.  `fn(n_loc, kind)` with kind in {"lanczos", "cg"} returns a
+    tensor (any device) or None to fall through to the device Philox generator."""
+    global _start_vector_hook
+    _start_vector_hook = fn
+
+
+def start_vector(n_loc: int, kind: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Standard-normal start vector on the GPU.  Reference: torch.randn at Lanczos.py:52, CG.py:58,121.
+
+    Reproducible under torch.manual_seed: the Philox key is torch's initial seed and the stream id a
+    per-process draw counter.  The counter is global-index based, so sharded runs draw the same vector.
+    """
+    global _draw_counter
+    ctx = context()
+    if out is None:
+        out = empty(n_loc, ctx.device)
+    if _start_vector_hook is not None:
+        v = _start_vector_hook(n_loc, kind)
+        if v is not None:
+            out.copy_(v.to(device=ctx.device, dtype=F64))
+            return out
+    _draw_counter += 1
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    _lib.check(ctx.lib.dsea_randn(ctx.handle, n_loc, seed, _draw_counter, ptr(out), stream_ptr()))
+    return out
