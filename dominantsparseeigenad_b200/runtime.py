@@ -41,16 +41,11 @@ class Context:
         self.device = torch.device("cuda", self.device_index)
         id_buf = None
         if world > 1:
-            idt = torch.zeros(128, dtype=torch.uint8)
+            from .sharding import broadcast_bytes
+            raw = (C.c_ubyte * 128)()
             if rank == 0:
-                raw = (C.c_ubyte * 128)()
                 _lib.check(self.lib.dsea_nccl_unique_id(raw))
-                idt = torch.tensor(list(raw), dtype=torch.uint8)
-            backend = torch.distributed.get_backend()
-            if backend == "nccl":
-                idt = idt.to(self.device)
-            torch.distributed.broadcast(idt, src=0)
-            id_buf = (C.c_ubyte * 128)(*idt.cpu().tolist())
+            id_buf = (C.c_ubyte * 128)(*broadcast_bytes(bytes(raw), 128, 0, self.device))
         handle = C.c_void_p()
         _lib.check(self.lib.dsea_ctx_create(self.device_index, rank, world, id_buf, C.byref(handle)))
         self.handle = handle
