@@ -22,6 +22,7 @@ PROTOTYPES = {
     "dsea_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dsea_ctx_destroy": (C.c_int, [C.c_void_p]),
     "dsea_ctx_rank": (C.c_int, [C.c_void_p]),
+    "dsea_ctx_p2p": (C.c_int, [C.c_void_p]),
     "dsea_ctx_world": (C.c_int, [C.c_void_p]),
     "dsea_launch_count": (C.c_int64, [C.c_void_p]),
     "dsea_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

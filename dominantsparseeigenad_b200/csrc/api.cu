@@ -52,11 +52,12 @@ void prof_end(dsea_ctx* ctx, int token, cudaStream_t st) {
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
-                    double* u, double* dot_out, double* work, cudaStream_t st) {
+                    double* u, double* dot_out, double* work, cudaStream_t st, bool prepushed = false,
+                    const double* remote_scale = nullptr) {
     switch (op->kind) {
         case DSEA_OP_TFIM:
             DSEA_ARG(param != nullptr, "TFIM operator needs the device scalar g");
-            return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st);
+            return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st, prepushed, remote_scale);
         case DSEA_OP_CSR:
             return csr_apply(ctx, op, param, shift, v, u, dot_out, st);
         case DSEA_OP_DENSE:
@@ -79,6 +80,7 @@ __global__ void lanczos_record_kernel(double* scal, const double* c, double* alp
         const double b2 = scal[S_BETA2];
         const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
         beta[i] = b;
+        scal[S_INVBETA] = (b > 0.0 && isfinite(b)) ? 1.0 / b : 0.0;
         if (!(b > 0.0) || !isfinite(b)) {
             if (scal[S_BREAK] == 0.0) {
                 scal[S_BREAK] = 1.0;
@@ -97,14 +99,18 @@ static int lanczos_start_impl(dsea_ctx* ctx, int64_t n, double* Q, cudaStream_t 
     return scale_by_inv_sqrt(ctx, n, Q, ctx->scal + S_BETA2, st);          // Lanczos.py:53
 }
 
+// `push_next`: pass 2 also stores the new (un-normalised) vector into the partners' arenas, so the next
+// matvec finds its remote shards already in place (the beta^2 allreduce that follows is the barrier).
 static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i, double* Q, const double* u,
-                             double* alpha, double* beta, cudaStream_t st) {
+                             double* alpha, double* beta, cudaStream_t st, bool push_next = false) {
     const int m = i + 1;
     DSEA_TRY(reorth_dots(ctx, n, ldq, m, Q, u, ctx->cvec, st));                       // c = Q^T u; alpha_i = c_i
     const bool more = (i < k - 1);
     if (more) {
         double* qnext = Q + (int64_t)m * ldq;
-        DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, u, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st));   // :61,66,69
+        PeerPtrs pp = peer_ptrs(ctx);
+        DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, u, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st,
+                               push_next ? &pp : nullptr));                                               // :61,66,69
     }
     lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, ctx->cvec, alpha, beta, i, more ? 1 : 0);
     count_launch(ctx);
@@ -203,6 +209,7 @@ int dsea_ctx_destroy(dsea_ctx* ctx) {
     return DSEA_OK;
 }
 
+int dsea_ctx_p2p(const dsea_ctx* ctx) { return ctx->p2p_ok ? 1 : 0; }
 int dsea_ctx_rank(const dsea_ctx* ctx) { return ctx->rank; }
 int dsea_ctx_world(const dsea_ctx* ctx) { return ctx->world; }
 int64_t dsea_launch_count(const dsea_ctx* ctx) { return ctx->launches; }
@@ -240,6 +247,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "tfim_run_bits")) ctx->tfim_run_bits = (int)value;
     else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (int)value;
+    else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else {
         set_error("unknown option %s", key);
         return DSEA_ERR_ARG;
@@ -259,6 +267,11 @@ int dsea_op_tfim(dsea_ctx* ctx, int N, dsea_op** out) {
     op->N = N;
     op->L = N - ctx->log2world;
     op->n_loc = (int64_t)1 << op->L;
+    int s = p2p_setup(ctx, op->n_loc);       // collective: every rank creates its operator at the same point
+    if (s != DSEA_OK) {
+        delete op;
+        return s;
+    }
     *out = op;
     return DSEA_OK;
 }
@@ -351,9 +364,12 @@ int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, i
     double* u = work;
     double* opwork = work + ldq;
     DSEA_TRY(lanczos_start_impl(ctx, n, Q, st));
+    const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->p2p_ok && ctx->arena_stride >= n;
     for (int i = 0; i < k; ++i) {
-        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, nullptr, opwork, st));   // Lanczos.py:54,71
-        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st));
+        const bool pre = fuse_push && i > 0;
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, nullptr, opwork, st, pre,
+                          ctx->scal + S_INVBETA));                                                   // Lanczos.py:54,71
+        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, fuse_push));
     }
     return lanczos_ritz_impl(ctx, n, ldq, k, which, Q, alpha, beta, evals, evec_min, evec_max, info_host, st);
 }

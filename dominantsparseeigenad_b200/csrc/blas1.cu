@@ -131,6 +131,25 @@ int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, 
     return DSEA_OK;
 }
 
+// ---- publish a shard to the partners' arenas (NVLink stores), used when no producing kernel can ----
+__global__ void __launch_bounds__(kThreads) push_kernel(const double* __restrict__ v, int64_t n, PeerPtrs peers) {
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 x = ldg2(v + 2 * i);
+        for (int j = 0; j < peers.n; ++j) stg2(peers.p[j] + 2 * i, x);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int j = 0; j < peers.n; ++j) peers.p[j][n - 1] = v[n - 1];
+}
+
+int push_to_peers(dsea_ctx* ctx, const double* v, int64_t n, cudaStream_t st) {
+    push_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(v, n, peer_ptrs(ctx));
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    return DSEA_OK;
+}
+
 // ---- Philox4x32-10 standard normals ----------------------------------------------------------------
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];

@@ -64,6 +64,12 @@ enum ScalarSlot {
     S_COUNT = 32
 };
 
+// peer pointers handed to producing kernels by value
+struct PeerPtrs {
+    double* p[kMaxRemote];
+    int n;
+};
+
 struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
 struct Profiler;  // optional per-kernel CUDA-event timing (api.cu)
 
@@ -92,6 +98,16 @@ struct dsea_ctx {
     int64_t launches = 0;
     const double* guard = nullptr;      // device flag consulted by operator kernels (set during CG)
     dsea::Profiler* prof = nullptr;     // non-null while per-kernel timing is enabled
+    // Peer-memory exchange arena (CUDA IPC over NVLink): slot j receives the shard of rank ^ (1 << j),
+    // written there directly by the PRODUCING kernel of that rank (fused compute + exchange).
+    double* arena = nullptr;
+    int64_t arena_stride = 0;           // doubles per slot
+    double* peer_slot[dsea::kMaxRemote] = {};   // partner j's slot j: where this rank's shard goes
+    void* peer_base[dsea::kMaxRemote] = {};
+    void* ipc_scratch = nullptr;
+    bool p2p_ok = false;
+    bool p2p_disabled = false;
+    bool fresh_collective = true;       // a collective completed since the arena was last read (WAR guard)
     // options
     int tfim_tile_bits = 13;
     int tfim_run_bits = 0;              // 0 = auto
@@ -120,8 +136,11 @@ namespace dsea {
 
 // ---- internal kernels' host launchers (each returns a DSEA status) ----------------------------
 // tfim.cu
+// `prepushed`: the input shard already sits in the partners' arenas (written by the producing kernel),
+// scaled there by 1 / *remote_scale^-1, i.e. the remote terms are multiplied by *remote_scale.
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
-               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st);
+               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st,
+               bool prepushed = false, const double* remote_scale = nullptr);
 int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st);
 int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
                  double* work, cudaStream_t st);
@@ -137,7 +156,7 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* 
                 cudaStream_t st);   // c_out[0..ncols) = Q^T u  (allreduced)
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u,
                   const double* c, double sign, double* r_out, double* norm2_out,
-                  cudaStream_t st);   // r = u + sign * Q c  (u may be NULL)
+                  cudaStream_t st, const PeerPtrs* peers = nullptr);   // r = u + sign * Q c  (u may be NULL)
 int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, cudaStream_t st);
 // blas1.cu
 int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st);
@@ -158,6 +177,16 @@ int comm_destroy(dsea_ctx* ctx);
 int comm_unique_id(void* id128);
 int allreduce_sum(dsea_ctx* ctx, double* buf, int64_t count, cudaStream_t st);
 int exchange_shards(dsea_ctx* ctx, const double* send, double* recv_base, int64_t n_loc, cudaStream_t st);
+int p2p_setup(dsea_ctx* ctx, int64_t n_loc);      // collective; falls back to NCCL send/recv if IPC is unavailable
+int p2p_teardown(dsea_ctx* ctx);
+int comm_barrier(dsea_ctx* ctx, cudaStream_t st);
+int push_to_peers(dsea_ctx* ctx, const double* v, int64_t n, cudaStream_t st);   // blas1.cu
+inline PeerPtrs peer_ptrs(const dsea_ctx* ctx) {
+    PeerPtrs pp;
+    pp.n = ctx->p2p_ok ? ctx->log2world : 0;
+    for (int j = 0; j < kMaxRemote; ++j) pp.p[j] = j < pp.n ? ctx->peer_slot[j] : nullptr;
+    return pp;
+}
 
 inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
 

@@ -124,7 +124,7 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
                      const double* __restrict__ c, double sign, int64_t n, int m, double* __restrict__ r,
-                     double* __restrict__ partials) {
+                     double* __restrict__ partials, const PeerPtrs peers) {
     extern __shared__ double cs[];                   // m coefficients (pre-multiplied by sign)
     __shared__ double red[32];
     for (int j = threadIdx.x; j < m; j += kRThreads) cs[j] = sign * c[j];
@@ -172,6 +172,10 @@ reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __
             }
             stg2(r + r0, x0);
             stg2(r + r1, x1);
+            for (int pj = 0; pj < peers.n; ++pj) {       // fused exchange: NVLink stores into the partners' arenas
+                stg2(peers.p[pj] + r0, x0);
+                stg2(peers.p[pj] + r1, x1);
+            }
         } else {
             const int64_t rows[4] = {r0, r0 + 1, r1, r1 + 1};
             double xv[4];
@@ -186,7 +190,10 @@ reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (rows[q] < n) r[rows[q]] = xv[q];
+                if (rows[q] < n) {
+                    r[rows[q]] = xv[q];
+                    for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][rows[q]] = xv[q];
+                }
             x0 = make_double2(xv[0], xv[1]);
             x1 = make_double2(xv[2], xv[3]);
         }
@@ -225,12 +232,15 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
 }
 
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, const double* c,
-                  double sign, double* r_out, double* norm2_out, cudaStream_t st) {
+                  double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
     const int grid = reorth_grid(ctx, n);
     const size_t smem = (size_t)m * sizeof(double);
     const int tok = prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
+    PeerPtrs pp;
+    pp.n = 0;
+    if (peers) pp = *peers;
     reorth_update_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
-                                                       norm2_out ? ctx->partials : nullptr);
+                                                       norm2_out ? ctx->partials : nullptr, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());

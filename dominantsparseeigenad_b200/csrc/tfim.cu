@@ -35,7 +35,9 @@ struct SweepParams {
     const double* w;        // dot partner (may alias v); nullptr = no dot
     const double* g;
     const double* shift;
-    const double* recv;     // nrecv buffers of n_loc doubles each
+    const double* recv;     // nrecv buffers, `recv_stride` doubles apart (NCCL recv buffers or the IPC arena)
+    const double* remote_scale;   // device scalar multiplying the remote terms (nullptr = 1)
+    uint64_t recv_stride;
     const double* guard;    // if non-null and != 0 the kernel is a no-op (CG converged)
     double* partials;
     uint64_t rank_off;      // rank << L
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
     const uint64_t nmask = (p.N >= 64) ? ~0ull : ((1ull << p.N) - 1ull);
     const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
     const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
+    const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
     double part = 0.0;
 
     for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -93,10 +96,15 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
                 a0 += y.x;
                 a1 += y.y;
             }
-            for (int j = 0; j < p.nrecv; ++j) {                 // top (remote) spin bits
-                const double2 y = ldg2(p.recv + (uint64_t)j * p.n_loc + gi);
-                a0 += y.x;
-                a1 += y.y;
+            if (p.nrecv > 0) {                                  // top (remote) spin bits
+                double r0 = 0.0, r1 = 0.0;
+                for (int j = 0; j < p.nrecv; ++j) {
+                    const double2 y = ldg2(p.recv + (uint64_t)j * p.recv_stride + gi);
+                    r0 += y.x;
+                    r1 += y.y;
+                }
+                a0 += rscale * r0;
+                a1 += rscale * r1;
             }
             if (MODE == MODE_ADJ) {
                 const double2 wv = ldg2(p.w + gi);
@@ -178,7 +186,7 @@ static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStrea
 //                mode_adj=true  -> out = -sum_s w[s] * sum_i v[s^(1<<i)].
 static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const double* g, const double* shift,
                     const double* v, double* u, const double* w, double* dot_out, double* work,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool prepushed = false, const double* remote_scale = nullptr) {
     Sweep sw[kMaxSweeps];
     const int L = op->L;
     int Tmax = ctx->tfim_tile_bits;
@@ -187,9 +195,17 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
     const int ns = plan_sweeps(L, Tmax, ctx->tfim_run_bits, sw);
     DSEA_ARG(ns > 0, "TFIM sweep plan failed");
     const int nrecv = ctx->log2world;
-    DSEA_ARG(nrecv == 0 || work != nullptr, "sharded TFIM matvec needs a work buffer");
+    const bool p2p = nrecv > 0 && ctx->p2p_ok && ctx->arena_stride >= (int64_t)op->n_loc;
+    DSEA_ARG(nrecv == 0 || p2p || work != nullptr, "sharded TFIM matvec needs a work buffer");
+    DSEA_ARG(!prepushed || p2p, "prepushed input without a peer arena");
 
-    if (nrecv > 0) {   // top-bit shards travel on the side stream while the local sweeps run
+    if (p2p) {         // partners' shards arrive in the arena by peer stores
+        if (!prepushed) {
+            if (!ctx->fresh_collective) DSEA_TRY(comm_barrier(ctx, st));   // partners finished reading the arena
+            DSEA_TRY(push_to_peers(ctx, v, op->n_loc, st));
+            DSEA_TRY(comm_barrier(ctx, st));                               // partners' stores have landed
+        }
+    } else if (nrecv > 0) {   // top-bit shards travel on the side stream while the local sweeps run
         DSEA_CUDA(cudaEventRecord(ctx->ev_ready, st));
         DSEA_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_ready, 0));
         DSEA_TRY(exchange_shards(ctx, v, work, op->n_loc, ctx->comm_stream));
@@ -206,7 +222,9 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.uout = u;
         p.g = g;
         p.shift = shift;
-        p.recv = work;
+        p.recv = p2p ? ctx->arena : work;
+        p.recv_stride = p2p ? (uint64_t)ctx->arena_stride : (uint64_t)op->n_loc;
+        p.remote_scale = (p2p && prepushed) ? remote_scale : nullptr;
         p.guard = ctx->guard;
         p.no_diag = (!mode_adj && g == nullptr) ? 1 : 0;
         p.nrecv = last ? nrecv : 0;
@@ -219,7 +237,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.b0 = sw[j].b0;
         p.ntiles = 1ull << (L - sw[j].T);
         int grid = (int)(p.ntiles < 2048 ? p.ntiles : 2048);
-        if (last && nrecv > 0) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
+        if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
         if (mode_adj) {
             p.w = w;
             p.partials = ctx->partials + total_partials;   // every sweep contributes partial sums
@@ -234,6 +252,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         }
     }
     prof_end(ctx, tok, st);
+    if (p2p) ctx->fresh_collective = false;    // the arena was just read: the next push needs a collective first
     if (want_dot) {
         DSEA_TRY(finalize_partials(ctx, total_partials, 1, dot_out, st));
         DSEA_TRY(allreduce_sum(ctx, dot_out, 1, st));
@@ -242,8 +261,9 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
 }
 
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
-               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st) {
-    return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st);
+               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st, bool prepushed,
+               const double* remote_scale) {
+    return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st, prepushed, remote_scale);
 }
 
 // u = (dH/dg) v: the same sweeps with g = 1 and the diagonal dropped (g == nullptr selects this).

@@ -55,6 +55,9 @@ class Context:
     def set_option(self, key: str, value: int) -> None:
         _lib.check(self.lib.dsea_ctx_set_option(self.handle, key.encode(), int(value)))
 
+    def p2p_enabled(self) -> bool:
+        return bool(self.lib.dsea_ctx_p2p(self.handle))
+
     def launch_count(self) -> int:
         return int(self.lib.dsea_launch_count(self.handle))
 
@@ -80,7 +83,8 @@ def context() -> Context:
     if _ctx is None:
         _ctx = Context()
         for key, env in (("tfim_tile_bits", "DSEA_TFIM_TILE_BITS"), ("tfim_run_bits", "DSEA_TFIM_RUN_BITS"),
-                         ("cg_check_every", "DSEA_CG_CHECK_EVERY"), ("reorth_ctas_per_sm", "DSEA_REORTH_CTAS")):
+                         ("cg_check_every", "DSEA_CG_CHECK_EVERY"), ("reorth_ctas_per_sm", "DSEA_REORTH_CTAS"),
+                         ("p2p", "DSEA_P2P")):
             if os.environ.get(env):
                 _ctx.set_option(key, int(os.environ[env]))
     return _ctx
