@@ -315,7 +315,9 @@ int dsea_op_destroy(dsea_op* op) {
 
 int64_t dsea_op_local_dim(const dsea_op* op) { return op->n_loc; }
 int64_t dsea_op_work_doubles(const dsea_op* op) {
-    return op->kind == DSEA_OP_TFIM ? (int64_t)op->ctx->log2world * op->n_loc : 0;
+    if (op->kind != DSEA_OP_TFIM) return 0;
+    if (op->ctx->p2p_ok && op->ctx->arena_stride >= op->n_loc) return 0;     // partners write into the IPC arena
+    return (int64_t)op->ctx->log2world * op->n_loc;                          // NCCL recv buffers
 }
 int64_t dsea_col_stride(int64_t n_loc) { return col_stride(n_loc); }
 
