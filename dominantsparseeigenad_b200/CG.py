@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 
 from . import runtime
-from .operators import Dot, as_operator, project
+from .operators import Dot, as_operator, project, scale
 from .runtime import context, dev_vec
 
 
@@ -57,7 +57,7 @@ class CGSubspace(torch.autograd.Function):
         rhs = _project_any(alpha, grad_x)                       # CG.py:67
         grad_b = CGSubspace.apply(A, rhs, alpha)                # :68
         grad_A = -grad_b[:, None] * x                           # :69
-        grad_alpha = -x * _dot_any(alpha, grad_x)               # :70
+        grad_alpha = -scale(_dot_any(alpha, grad_x), x)         # :70
         return grad_A, grad_b, grad_alpha
 
 
@@ -89,7 +89,7 @@ def make_cg_subspace_sparse(op, Aadjoint_to_gadjoint=None):
             rhs = _project_any(alpha, grad_x)                               # CG.py:132
             grad_b = CGSubspaceSparse.apply(g, E0, rhs, alpha)              # :133
             v1, v2 = -grad_b, x                                             # :134
-            grad_alpha = -x * _dot_any(alpha, grad_x)                       # :135
+            grad_alpha = -scale(_dot_any(alpha, grad_x), x)                 # :135
             grad_E0 = -_dot_any(v1, v2)                                     # :136
             grad_g = _param_adjoint(op, Aadjoint_to_gadjoint, v1, v2, g)    # :137
             return grad_g, grad_E0, grad_b, grad_alpha
@@ -145,7 +145,7 @@ def setCGSubspaceSparse(A, Aadjoint_to_gadjoint):
             rhs = _project_any(alpha, grad_x)
             grad_b = CGSubspaceSparse.apply(g, E0, rhs, alpha)              # looked up at call time, CG.py:131
             v1, v2 = -grad_b, x
-            grad_alpha = -x * _dot_any(alpha, grad_x)
+            grad_alpha = -scale(_dot_any(alpha, grad_x), x)
             grad_E0 = -_dot_any(v1, v2)
             grad_g = _param_adjoint(op, Aadjoint_to_gadjoint, v1, v2, g)
             return grad_g, grad_E0, grad_b, grad_alpha

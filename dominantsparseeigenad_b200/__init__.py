@@ -7,6 +7,6 @@ the C ABI of include/dsea.h (libdsea.so).  There is no CPU fallback.
 from . import _lib, runtime                                        # noqa: F401
 from . import CG, Lanczos, symeig                                  # noqa: F401
 from .operators import (CallbackOperator, DenseOperator, SparseMatrixOperator, TFIM, dot,  # noqa: F401
-                        project)
+                        project, scale)
 
 __version__ = "0.1.0"

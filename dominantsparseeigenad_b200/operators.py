@@ -49,11 +49,41 @@ class Dot(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         a, b = ctx.saved_tensors
-        return go * b, go * a
+        return scale(go, b), scale(go, a)
 
 
 def dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return Dot.apply(a, b)
+
+
+class Scale(torch.autograd.Function):
+    """s * v for a REPLICATED scalar s (0-dim or one element) and a SHARDED vector v.
+
+    A plain `s * v` would let torch reduce the gradient of s with a rank-local sum; here it is the
+    global inner product (allreduced inside libdsea), so replicated scalars stay replicated in every
+    order of differentiation.  With one rank this is exactly torch's broadcasting multiply.
+    """
+
+    @staticmethod
+    def forward(ctx, s, v):
+        ctx.save_for_backward(s, v)
+        return s.reshape(()).to(v.device) * v
+
+    @staticmethod
+    def backward(ctx, go):
+        s, v = ctx.saved_tensors
+        grad_s = Dot.apply(go, v).reshape(s.shape).to(s.device) if ctx.needs_input_grad[0] else None
+        grad_v = Scale.apply(s, go) if ctx.needs_input_grad[1] else None
+        return grad_s, grad_v
+
+
+def scale(s, v: torch.Tensor) -> torch.Tensor:
+    """Shard-safe `s * v`; python floats and non-differentiable scalars take the cheap path."""
+    if not isinstance(s, torch.Tensor):
+        return s * v
+    if s.numel() != 1:
+        raise ValueError("scale() expects a single-element scalar")
+    return Scale.apply(s, v)
 
 
 class Project(torch.autograd.Function):
@@ -72,7 +102,7 @@ class Project(torch.autograd.Function):
     def backward(ctx, go):
         psi, b = ctx.saved_tensors
         grad_b = Project.apply(psi, go)
-        grad_psi = -(dot(psi, b) * go) - dot(go, psi) * b
+        grad_psi = -scale(dot(psi, b), go) - scale(dot(go, psi), b)
         return grad_psi, grad_b
 
 
@@ -191,7 +221,7 @@ class _TFIMAdjoint(torch.autograd.Function):
     def backward(ctx, go):
         v1, v2 = ctx.saved_tensors
         m = ctx.model
-        return None, go * _PHpg.apply(m, v2), go * _PHpg.apply(m, v1)
+        return None, scale(go, _PHpg.apply(m, v2)), scale(go, _PHpg.apply(m, v1))
 
 
 class _TFIMMatvec(torch.autograd.Function):

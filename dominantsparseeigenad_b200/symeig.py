@@ -17,7 +17,7 @@ import torch
 from . import CG as _CG
 from . import _lib
 from .CG import _dot_any, _param_adjoint, _project_any
-from .operators import as_operator
+from .operators import as_operator, scale
 
 
 class DominantSymeig(torch.autograd.Function):
@@ -40,7 +40,7 @@ class DominantSymeig(torch.autograd.Function):
         Aprime = A - eigval * torch.eye(A.shape[0], device=A.device, dtype=A.dtype)     # symeig.py:25
         b = _project_any(eigvector, grad_eigvector)                                      # :27
         lambda0 = _CG.CGSubspace.apply(Aprime, b, eigvector)                             # :28
-        grad_A = (grad_eigval * eigvector - lambda0)[:, None] * eigvector                # :29
+        grad_A = (scale(grad_eigval, eigvector) - lambda0)[:, None] * eigvector          # :29
         return grad_A, None, None
 
 
@@ -84,7 +84,7 @@ def setDominantSparseSymeig(A, Aadjoint_to_gadjoint):
             g, eigval, eigvector = ctx.saved_tensors
             b = _project_any(eigvector, grad_eigvector)                                # symeig.py:80
             lambda0 = cg(g, eigval, b, eigvector)                                      # :81
-            v1, v2 = grad_eigval * eigvector - lambda0, eigvector                      # :82-83
+            v1, v2 = scale(grad_eigval, eigvector) - lambda0, eigvector                # :82-83
             grad_g = _param_adjoint(ctx.op, Aadjoint_to_gadjoint, v1, v2, g)           # :84
             return grad_g, None, None, None
 

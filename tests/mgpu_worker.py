@@ -79,6 +79,16 @@ def main():
     logF = torch.log(dsea.dot(psi0.detach(), psi0))
     dlogF, = torch.autograd.grad(logF, m.g, create_graph=True)
     d2logF, = torch.autograd.grad(dlogF, m.g)
+    if os.environ.get("DSEA_DIAG"):
+        for rep in range(3):
+            m.g = torch.tensor([g], dtype=torch.float64, device=dev, requires_grad=True)
+            E0b, psib = dsea.symeig.DominantSparseSymeig.apply(m.g, k, m.dim, dev)
+            lf = torch.log(dsea.dot(psib.detach(), psib))
+            d1, = torch.autograd.grad(lf, m.g, create_graph=True)
+            d2, = torch.autograd.grad(d1, m.g)
+            if rank == 0:
+                print("DIAG chiF", world, rt.p2p_enabled(), -d2.item(), achi, d1.item(),
+                      dsea.runtime.stats["cg_iters"][-4:], flush=True)
     assert rel(-d2logF.item(), achi) < 1e-6, (-d2logF.item(), achi)
     # every rank holds identical replicated scalars
     t = torch.tensor([E0.item(), dE0.item(), d2E0.item()], dtype=torch.float64, device=dev)
