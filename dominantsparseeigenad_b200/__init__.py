@@ -5,7 +5,7 @@ Drop-in for the hot path of buwantaiji/DominantSparseEigenAD: the modules `symei
 the C ABI of include/dsea.h (libdsea.so).  There is no CPU fallback.
 """
 from . import _lib, runtime                                        # noqa: F401
-from . import CG, Lanczos, symeig                                  # noqa: F401
+from . import CG, Lanczos, eig, symeig                             # noqa: F401
 from .operators import (CallbackOperator, DenseOperator, SparseMatrixOperator, TFIM, dot,  # noqa: F401
                         project, scale)
 

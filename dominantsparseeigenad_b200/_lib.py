@@ -52,6 +52,11 @@ PROTOTYPES = {
                                     c_double_p, c_stream]),
     "dsea_lanczos_ritz": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                     c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int64), c_stream]),
+    "dsea_arnoldi_start": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_stream]),
+    "dsea_arnoldi_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
+                                    c_stream]),
+    "dsea_combine": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                               c_stream]),
     "dsea_cg_work_doubles": (C.c_int64, [C.c_void_p]),
     "dsea_cg": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                           C.c_double, C.c_int64, C.POINTER(C.c_int64), c_stream]),

@@ -141,6 +141,15 @@ static int lanczos_ritz_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int w
 
 static inline int64_t col_stride(int64_t n) { return (n + 15) & ~(int64_t)15; }
 
+// ---- Arnoldi bookkeeping (single thread): H[0..i, i] = c1 + c2, H[i+1, i] = |r| -----------------
+__global__ void arnoldi_record_kernel(double* scal, const double* c1, const double* c2, double* hcol, int i) {
+    for (int j = 0; j <= i; ++j) hcol[j] = c1[j] + c2[j];
+    const double b2 = scal[S_BETA2];
+    const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
+    hcol[i + 1] = b;
+    if (!(b > 0.0) || !isfinite(b)) scal[S_BETA2] = 0.0;      // invariant subspace: next column is zero
+}
+
 }  // namespace dsea
 
 using namespace dsea;
@@ -397,6 +406,45 @@ int dsea_lanczos_ritz(dsea_ctx* ctx, int64_t n_loc, int k, int which, const doub
     DSEA_ARG(aligned16(Q) && aligned16(evec_min) && aligned16(evec_max), "buffers must be 16-byte aligned");
     return lanczos_ritz_impl(ctx, n_loc, col_stride(n_loc), k, which, Q, alpha, beta, evals, evec_min, evec_max,
                              info_host, (cudaStream_t)stream);
+}
+
+// ---- Arnoldi (non-symmetric family, eig.py) ---------------------------------------------------------
+int dsea_arnoldi_start(dsea_ctx* ctx, int64_t n_loc, double* Q, double* norm_out, void* stream) {
+    DSEA_ARG(ctx && Q && aligned16(Q), "bad Q");
+    cudaStream_t st = (cudaStream_t)stream;
+    DSEA_TRY(dot(ctx, n_loc, Q, Q, ctx->scal + S_BETA2, st));
+    if (norm_out) DSEA_CUDA(cudaMemcpyAsync(norm_out, ctx->scal + S_BETA2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return scale_by_inv_sqrt(ctx, n_loc, Q, ctx->scal + S_BETA2, st);
+}
+
+int dsea_arnoldi_step(dsea_ctx* ctx, int64_t n_loc, int m, int i, double* Q, const double* u, double* H,
+                      void* stream) {
+    DSEA_ARG(ctx && Q && u && H, "NULL argument");
+    DSEA_ARG(i >= 0 && i < m && m < kMaxK, "Arnoldi step index out of range");
+    DSEA_ARG(aligned16(Q) && aligned16(u), "buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ldq = col_stride(n_loc);
+    const int cols = i + 1;
+    double* qnext = Q + (int64_t)cols * ldq;
+    double* c1 = ctx->cvec;
+    double* c2 = ctx->yvec;
+    // classical Gram-Schmidt with one re-orthogonalisation sweep (CGS2, as ARPACK's DGKS refinement)
+    DSEA_TRY(reorth_dots(ctx, n_loc, ldq, cols, Q, u, c1, st));
+    DSEA_TRY(reorth_update(ctx, n_loc, ldq, cols, Q, u, c1, -1.0, qnext, nullptr, st));
+    DSEA_TRY(reorth_dots(ctx, n_loc, ldq, cols, Q, qnext, c2, st));
+    DSEA_TRY(reorth_update(ctx, n_loc, ldq, cols, Q, qnext, c2, -1.0, qnext, ctx->scal + S_BETA2, st));
+    arnoldi_record_kernel<<<1, 1, 0, st>>>(ctx->scal, c1, c2, H + (int64_t)i * (m + 1), i);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    return scale_by_inv_sqrt(ctx, n_loc, qnext, ctx->scal + S_BETA2, st);
+}
+
+int dsea_combine(dsea_ctx* ctx, int64_t n_loc, int m, const double* Q, const double* coef, const double* add,
+                 double* out, void* stream) {
+    DSEA_ARG(ctx && Q && coef && out, "NULL argument");
+    DSEA_ARG(m >= 1 && m <= kMaxK, "m out of range");
+    DSEA_ARG(aligned16(Q) && aligned16(out) && aligned16(add), "buffers must be 16-byte aligned");
+    return reorth_update(ctx, n_loc, col_stride(n_loc), m, Q, add, coef, 1.0, out, nullptr, (cudaStream_t)stream);
 }
 
 // ---- CG -----------------------------------------------------------------------------------------------

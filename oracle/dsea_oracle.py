@@ -23,7 +23,7 @@ __all__ = [
     "SeededDraws", "ListDraws", "tfim_flip_table", "tfim_diagonal", "tfim_diagonal_closed_form",
     "TFIMOracle", "lanczos_basis", "extreme_eigpair", "cg_solve", "make_sparse_primitives",
     "dense_dominant_symeig", "tfim_analytic", "tfim_energy_derivatives", "tfim_fidelity_susceptibility",
-    "Schrodinger1DOracle", "MatvecCounter",
+    "Schrodinger1DOracle", "MatvecCounter", "dominant_eig_triple", "dominant_eig_backward", "mps_transfer_matrix",
 ]
 
 F64 = torch.float64
@@ -419,3 +419,40 @@ class Schrodinger1DOracle:
         Dom, _ = make_sparse_primitives(self.Hsparse, self.Hadjoint_to_padjoint, draw)
         _, psi0 = Dom.apply(self.potential, k, self.N)
         return 1.0 - (psi0.abs() * self.target).sum()
+
+
+# ----------------------------------------------------------------------------------------------
+# Non-symmetric family (eig.py).  The arithmetic of the reference lives in scipy (ARPACK `eigs`,
+# `gmres`; scipy is un-pinned in the reference's requirements.txt:2 — 1.18.1 in this image), so the
+# restatement keeps exactly those call sites and the reference's normalisation / adjoint formulas.
+# ----------------------------------------------------------------------------------------------
+def dominant_eig_triple(A: np.ndarray, k: int, which: str = "LM"):
+    """(eigval, left, right) with l.r = 1 and |r| = 1.  Restates eig.py:28-39."""
+    from scipy.sparse import linalg as sla
+    wr, vr = sla.eigs(A, k=1, which=which, ncv=k)                         # eig.py:29
+    wl, vl = sla.eigs(A.T, k=1, which=which, ncv=k)                       # :30
+    assert np.allclose(wr.imag, 0.0), "the desired eigenvalue must be real"   # :31
+    r = vr[:, 0].real
+    l = vl[:, 0].real
+    l = l / np.dot(l, r)                                                  # :36
+    return wr.real, l, r
+
+
+def dominant_eig_backward(A: np.ndarray, eigval, l, r, grad_eigval, grad_l, grad_r):
+    """grad_A for the triple above.  Restates eig.py:45-60 (two GMRES solves, three outer products)."""
+    from scipy.sparse import linalg as sla
+    n = A.shape[0]
+    Ap = A - eigval * np.eye(n)
+    b = grad_l - r * np.dot(l, grad_l)                                    # eig.py:53
+    lam_l, _ = sla.gmres(Ap, b, rtol=1e-12, atol=1e-12)                   # :54 (tol= renamed rtol= in scipy>=1.12)
+    Ap = A.T - eigval * np.eye(n)
+    b = grad_r - l * np.dot(r, grad_r)                                    # :56
+    lam_r, _ = sla.gmres(Ap, b, rtol=1e-12, atol=1e-12)                   # :57
+    return grad_eigval * l[:, None] * r - l[:, None] * lam_l - lam_r[:, None] * r   # :58-60
+
+
+def mps_transfer_matrix(D: int, d: int, seed: int) -> np.ndarray:
+    """The D^2 x D^2 'Gong' transfer matrix of a random real MPS tensor (test_gradient.py:6-9)."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((d, D, D))
+    return np.einsum("kij,kmn->imjn", A, A).reshape(D * D, D * D)

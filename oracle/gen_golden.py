@@ -72,7 +72,47 @@ def _sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def _eig_section(orc):
+    # ------------------------------------------------------------------ 7. non-symmetric family (eig.py)
+    import scipy.sparse.linalg as _sla
+    _orig_gmres = _sla.gmres
+
+    def _gmres_compat(A, b, *a, tol=None, **kw):          # scipy >= 1.12 renamed tol -> rtol (eig.py:54,57)
+        if tol is not None:
+            kw.setdefault("rtol", tol)
+        return _orig_gmres(A, b, *a, **kw)
+
+    _sla.gmres = _gmres_compat
+    from DominantSparseEigenAD.eig import DominantEig as RefDominantEig
+    eg = {}
+    for tag, D, kk in (("D5", 5, 25), ("D8", 8, 40)):
+        G = orc.mps_transfer_matrix(D, 2, 2024 + D)
+        Gt = torch.from_numpy(G).requires_grad_(True)
+        rng = np.random.default_rng(99 + D)
+        a = float(rng.standard_normal())
+        M = torch.from_numpy(rng.standard_normal((D * D, D * D)))
+        lam, l, r = RefDominantEig.apply(Gt, kk)
+        l0, r0 = l, r
+        # gauge-invariant loss (invariant under r -> -r, l -> -l):  a*lambda + l^T M r   (test_gradient.py:16-19)
+        loss = a * lam + l0.matmul(M).matmul(r0)
+        gA, = torch.autograd.grad(loss, Gt)
+        olam, ol, orr = orc.dominant_eig_triple(G, kk)
+        l, r = l.detach(), r.detach()
+        sgn = np.sign(np.dot(orr, r.numpy()))
+        assert abs(olam[0] - lam.item()) < 1e-12 * abs(lam.item())
+        assert np.allclose(sgn * orr, r.numpy(), atol=1e-10) and np.allclose(sgn * ol, l.numpy(), atol=1e-10)
+        ogA = orc.dominant_eig_backward(G, lam.detach().numpy(), l.numpy(), r.numpy(), np.array([a]),
+                                        (M @ r.numpy()), (M.numpy().T @ l.numpy()))
+        assert np.allclose(ogA, gA.numpy(), atol=1e-9)
+        eg.update({tag + "_G": G, tag + "_k": np.array(kk), tag + "_a": np.array(a), tag + "_M": M.numpy(),
+                   tag + "_lam": lam.detach().numpy(), tag + "_l": l.numpy(), tag + "_r": r.numpy(),
+                   tag + "_loss": np.array(loss.item()), tag + "_gradA": gA.numpy()})
+        print("eig", tag, lam.item(), loss.item(), np.abs(gA.numpy()).max())
+    np.savez_compressed(os.path.join(OUT, "dominant_eig.npz"), **eg)
+
+
 def main():
+    only_eig = "--only-eig" in sys.argv
     _install_shims()
     import contextlib
     import io
@@ -87,6 +127,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     f32round = lambda x: float(np.float64(np.float32(x)))
 
+    if only_eig:
+        return _eig_section(orc)
     # ------------------------------------------------------------------ 1. integer tables
     tables = {}
     for N in (3, 4, 10, 12, 16):
@@ -238,6 +280,7 @@ def main():
         print("config1", variant, loss.item(), grad.norm().item())
     sch["target"] = mine.target.numpy()
     np.savez_compressed(os.path.join(OUT, "schrodinger1d.npz"), **sch)
+    _eig_section(orc)
     print("golden vectors written to", OUT)
 
 

@@ -457,3 +457,89 @@ def test_device_randn_is_standard_normal(dsea):
     torch.manual_seed(1234)
     dsea.runtime._draw_counter = 0
     assert torch.equal(c, dsea.runtime.start_vector(1000, "cg"))
+
+
+# ------------------------------------------------------------------------------------------------
+# non-symmetric family (eig.py)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["D5", "D8"])
+def test_dominant_eig_golden(dsea, golden, tag):
+    """Forward triple and grad_A against the reference's own output (ARPACK + GMRES on the CPU)."""
+    from dominantsparseeigenad_b200.eig import DominantEig
+    e = golden("dominant_eig.npz")
+    G = torch.from_numpy(e[tag + "_G"]).requires_grad_(True)
+    k, a, M = int(e[tag + "_k"]), float(e[tag + "_a"]), torch.from_numpy(e[tag + "_M"])
+    lam, l, r = DominantEig.apply(G, k)
+    assert lam.shape == (1,) and l.device.type == "cpu"
+    assert rel(lam.item(), float(e[tag + "_lam"][0])) < EVAL_RTOL
+    sgn = np.sign(np.dot(r.detach().numpy(), e[tag + "_r"]))
+    assert np.abs(sgn * r.detach().numpy() - e[tag + "_r"]).max() < 1e-8
+    assert np.abs(sgn * l.detach().numpy() - e[tag + "_l"]).max() < 1e-8 * np.abs(e[tag + "_l"]).max()
+    assert abs(torch.dot(l, r).item() - 1.0) < 1e-12 and abs(torch.dot(r, r).item() - 1.0) < 1e-12
+    loss = a * lam + l.matmul(M).matmul(r)
+    gA, = torch.autograd.grad(loss, G)
+    assert rel(loss.item(), float(e[tag + "_loss"])) < 1e-9
+    assert np.abs(gA.numpy() - e[tag + "_gradA"]).max() < GRAD_RTOL * np.abs(e[tag + "_gradA"]).max()
+
+
+def test_dominant_eig_reference_gradcheck(dsea, orc):
+    """test_gradient.py:5-22 re-hosted: finite-difference gradcheck of DominantEig on a 25x25 transfer matrix."""
+    from dominantsparseeigenad_b200.eig import DominantEig
+    Gong = torch.from_numpy(orc.mps_transfer_matrix(5, 2, 7)).requires_grad_()
+    torch.manual_seed(5)
+    a = torch.randn(1, dtype=F64)
+    Arandom = torch.randn(25, 25, dtype=F64)
+
+    def func(A):
+        eigval, l, r = DominantEig.apply(A, 25)
+        return a * eigval + l.matmul(Arandom).matmul(r)
+
+    assert torch.autograd.gradcheck(func, (Gong,), eps=1e-6, atol=1e-5, rtol=1e-4, nondet_tol=1e-7)
+
+
+def test_dominant_sparse_eig_matches_dense(dsea, orc):
+    """eig.py:64-152 / TFIM_vumps/general.py:57-75 shape: scipy LinearOperators + numpy adjoint callback."""
+    import scipy.sparse.linalg as sla
+    from dominantsparseeigenad_b200 import eig
+    D, d = 6, 2
+    rng = np.random.default_rng(11)
+    A0 = rng.standard_normal((d, D, D))
+    A = torch.from_numpy(A0).requires_grad_(True)
+    Gong_t = torch.einsum("kij,kmn->imjn", A, A).reshape(D * D, D * D)
+    lam_d, l_d, r_d = eig.DominantEig.apply(Gong_t, 30)
+    M = torch.from_numpy(rng.standard_normal((D * D, D * D)))
+    loss_d = 0.3 * lam_d + l_d.matmul(M).matmul(r_d)
+    g_dense, = torch.autograd.grad(loss_d, A)
+
+    fr = lambda v: np.einsum("kij,kmn,jn->im", A0, A0, v.reshape(D, D)).reshape(-1)
+    fl = lambda v: np.einsum("kij,kmn,im->jn", A0, A0, v.reshape(D, D)).reshape(-1)
+    Gong = sla.LinearOperator((D * D, D * D), matvec=fr)
+    GongT = sla.LinearOperator((D * D, D * D), matvec=fl)
+
+    def adj(grad_Gong):                                   # general.py:67-74
+        gA = np.zeros((d, D, D))
+        for u, v in grad_Gong:
+            um, vm = u.reshape(D, D), v.reshape(D, D)
+            gA = gA + np.einsum("im,jn,kmn->kij", um, vm, A0) + np.einsum("mi,nj,kmn->kij", um, vm, A0)
+        return torch.from_numpy(gA)
+
+    eig.setDominantSparseEig(Gong, GongT, adj)
+    A2 = torch.from_numpy(A0).requires_grad_(True)
+    lam_s, l_s, r_s = eig.DominantSparseEig.apply(A2, 30)
+    loss_s = 0.3 * lam_s + l_s.matmul(M).matmul(r_s)
+    g_sparse, = torch.autograd.grad(loss_s, A2)
+    assert rel(lam_s.item(), lam_d.item()) < EVAL_RTOL and rel(loss_s.item(), loss_d.item()) < 1e-9
+    assert (g_sparse - g_dense).abs().max().item() < GRAD_RTOL * g_dense.abs().max().item()
+
+
+def test_dominant_eig_restarts_when_k_is_small(dsea):
+    """k << n: the explicitly restarted Arnoldi must still converge to ARPACK-level accuracy."""
+    from dominantsparseeigenad_b200.eig import DominantEig
+    torch.manual_seed(9)
+    n = 400
+    A = torch.rand(n, n, dtype=F64) / n + torch.diag(torch.linspace(0.0, 1.0, n, dtype=F64))
+    lam, l, r = DominantEig.apply(A, 20)
+    w = torch.linalg.eigvals(A)
+    ref = w[torch.argmax(w.abs())]
+    assert abs(ref.imag.item()) < 1e-12 and rel(lam.item(), ref.real.item()) < EVAL_RTOL
+    assert (A @ r - lam * r).norm().item() < 1e-9 and (A.T @ l - lam * l).norm().item() < 1e-9 * l.norm().item()
