@@ -88,7 +88,7 @@ def dominant_eigpair(apply, n: int, k: int, which: str = "LM"):
         # an (almost) invariant subspace shows up as a tiny sub-diagonal entry: truncate there
         sub = torch.diagonal(Hbar, offset=-1)[:k]
         scale_h = Hbar.abs().max().item()
-        small = (sub.abs() <= 1e-14 * scale_h).nonzero()
+        small = (sub.abs() <= 1e-12 * scale_h).nonzero()
         m = int(small[0]) + 1 if small.numel() else k
         w, Y = torch.linalg.eig(Hbar[:m, :m])
         j = _select(w, which)
@@ -125,7 +125,7 @@ def gmres_solve(apply, b: torch.Tensor, restart: int = 64, rtol: float = GMRES_R
     for _ in range(maxiter):
         Q, ldq, Hbar, beta = _arnoldi(apply, n, m, r)
         sub = torch.diagonal(Hbar, offset=-1)[:m]
-        small = (sub.abs() <= 1e-15 * Hbar.abs().max().item()).nonzero()
+        small = (sub.abs() <= 1e-12 * Hbar.abs().max().item()).nonzero()
         mm = int(small[0]) + 1 if small.numel() else m
         rhs = torch.zeros(mm + 1, 1, dtype=F64)
         rhs[0, 0] = beta
@@ -177,6 +177,12 @@ def _backward_vectors(apply_A_shifted, apply_AT_shifted, l, r, grad_l, grad_r):
     lam_l0 = gmres_solve(apply_A_shifted, b)                              # :54,140
     b = grad_r - l * torch.dot(r, grad_r)                                 # :56,143
     lam_r0 = gmres_solve(apply_AT_shifted, b)                             # :57,144
+    # Gauge.  (A - lambda) is singular: solutions differ by multiples of its null vector (r, resp. l).
+    # scipy's GMRES from x0 = 0 stays inside the Krylov space of b, which lies in range(A - lambda) =
+    # l-perp (resp. r-perp), so the reference implicitly returns the solution with l . x = 0 (r . x = 0).
+    # We impose that condition explicitly so that it also holds after Krylov breakdown / restarts.
+    lam_l0 = lam_l0 - r * torch.dot(l, lam_l0)
+    lam_r0 = lam_r0 - l * torch.dot(r, lam_r0)
     return lam_l0, lam_r0
 
 
