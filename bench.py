@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spins", type=int, default=0, help="override N (default 24 + log2 gpus)")
-    ap.add_argument("--k", type=int, default=200)
+    ap.add_argument("--k", type=int, default=200, help="Lanczos vectors; 0 = largest k <= 200 whose fp64 basis fits HBM")
     ap.add_argument("--g", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-spins", type=int, default=SAMPLE_N)
@@ -198,6 +198,15 @@ def main():
     log2w = max(world, 1).bit_length() - 1
     N = args.spins or (24 + log2w)
     k = args.k
+    if args.impl == "ours" and k <= 0:
+        # capacity policy: the fp64 basis is k * 8 * n_loc bytes per GPU; keep 16 vectors + 2 GB
+        # for the matvec / CG work space, the peer arena and the eigenvector.
+        torch.cuda.set_device(local_rank)
+        free_b, _ = torch.cuda.mem_get_info()
+        vec_b = 8 * 2 ** (N - log2w)
+        k = int(max(2, min(200, (free_b - 16 * vec_b - 2e9) // vec_b)))
+    elif k <= 0:
+        k = 200
     config = {"workload": f"tfim_N{N}_k{k}_E0_plus_dE0dg", "spins": N, "lanczos_vectors": k, "g": args.g,
               "sharding": f"top{log2w}bits_x{world}" if world > 1 else "single_gpu",
               "l2": "inputs_exceed_l2 (Lanczos basis %.1f GB per GPU)" % (k * 2.0 ** (N - log2w) * 8 / 1e9),
