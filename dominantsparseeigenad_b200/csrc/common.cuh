@@ -111,6 +111,7 @@ struct dsea_ctx {
     // options
     int tfim_tile_bits = 13;
     int tfim_run_bits = 0;              // 0 = auto
+    int tfim_pipeline = 1;              // persistent double-buffered sweep kernel for full 2^13 tiles
     int cg_check_every = 16;
     int reorth_ctas_per_sm = 4;
 };

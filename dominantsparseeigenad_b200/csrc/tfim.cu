@@ -137,6 +137,139 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
     }
 }
 
+// ---- fast path: persistent, double-buffered, register-blocked sweep for full 2^13 tiles -------------
+// One CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Tile i+1 is fetched with cp.async
+// (LDGSTS, 16 B) into the second 64 KB buffer while tile i is being reduced, so the HBM stream never
+// waits for the shared-memory phase.  A thread owns 8 pairs = 16 amplitudes whose tile bits {0,10,11,12}
+// vary: flips of those four bits are register moves; only tile bits 1..9 are served by shared memory
+// (9 conflict-free LDS.128 per pair instead of 12), which brings the crossbar traffic of a tile below
+// its HBM time.
+constexpr int kPipeT = 13;
+constexpr int kPipeThreads = 512;
+constexpr int kPipePairs = (1 << (kPipeT - 1)) / kPipeThreads;   // 8
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
+    extern __shared__ __align__(16) double bufs[];               // 2 x 2^13 doubles
+    __shared__ double red[32];
+    if (p.guard && *p.guard != 0.0) return;
+    constexpr int T = kPipeT;
+    const int c = p.c;
+    const uint32_t cmask = (1u << c) - 1u;
+    const int midbits = p.hshift - c;
+    const uint64_t nmask = (p.N >= 64) ? ~0ull : ((1ull << p.N) - 1ull);
+    const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
+    const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
+    const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
+    const int bstart = p.b0 > 1 ? p.b0 : 1;
+    double part = 0.0;
+
+    uint32_t e[kPipePairs];                                      // tile offsets of this thread's pairs
+#pragma unroll
+    for (int j = 0; j < kPipePairs; ++j) e[j] = 2u * (threadIdx.x + kPipeThreads * j);
+
+    auto tile_base = [&](uint64_t t) -> uint64_t {
+        const uint64_t t_mid = t & ((1ull << midbits) - 1ull), t_up = t >> midbits;
+        return (t_mid << c) | (t_up << (p.hshift + T - c));
+    };
+    auto gidx = [&](uint64_t base, uint32_t ee) -> uint64_t {
+        return base | (ee & cmask) | ((uint64_t)(ee >> c) << p.hshift);
+    };
+    auto prefetch = [&](uint64_t t, double* buf) {
+        const uint64_t base = tile_base(t);
+#pragma unroll
+        for (int j = 0; j < kPipePairs; ++j) cp_async16(buf + e[j], p.v + gidx(base, e[j]));
+        cp_async_commit();
+    };
+
+    uint64_t t = blockIdx.x;
+    int stage = 0;
+    if (t < p.ntiles) prefetch(t, bufs);
+    for (; t < p.ntiles; t += gridDim.x, stage ^= 1) {
+        const double* buf = bufs + ((size_t)stage << T);
+        const uint64_t tn = t + gridDim.x;
+        const uint64_t base = tile_base(t);
+        if (tn < p.ntiles) prefetch(tn, bufs + ((size_t)(stage ^ 1) << T));
+        double2 ui[kPipePairs];
+        if (MODE == MODE_ACCUM) {                                 // issue these HBM loads before waiting
+#pragma unroll
+            for (int j = 0; j < kPipePairs; ++j) ui[j] = ldg2(p.uin + gidx(base, e[j]));
+        }
+        if (tn < p.ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+
+        double2 x[kPipePairs], a[kPipePairs];
+#pragma unroll
+        for (int j = 0; j < kPipePairs; ++j) x[j] = *reinterpret_cast<const double2*>(buf + e[j]);
+#pragma unroll
+        for (int j = 0; j < kPipePairs; ++j) {                    // register-resident flips
+            a[j] = (p.b0 == 0) ? make_double2(x[j].y, x[j].x) : make_double2(0.0, 0.0);   // tile bit 0
+#pragma unroll
+            for (int jb = 0; jb < 3; ++jb) {                      // tile bits 10, 11, 12
+                a[j].x += x[j ^ (1 << jb)].x;
+                a[j].y += x[j ^ (1 << jb)].y;
+            }
+        }
+        for (int b = bstart; b < 10; ++b) {                       // tile bits 1..9 from shared memory
+#pragma unroll
+            for (int j = 0; j < kPipePairs; ++j) {
+                const double2 y = *reinterpret_cast<const double2*>(buf + (e[j] ^ (1u << b)));
+                a[j].x += y.x;
+                a[j].y += y.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kPipePairs; ++j) {
+            const uint64_t gi = gidx(base, e[j]);
+            double a0 = a[j].x, a1 = a[j].y;
+            if (p.nrecv > 0) {                                    // top (remote) spin bits
+                double r0 = 0.0, r1 = 0.0;
+                for (int q = 0; q < p.nrecv; ++q) {
+                    const double2 y = ldg2(p.recv + (uint64_t)q * p.recv_stride + gi);
+                    r0 += y.x;
+                    r1 += y.y;
+                }
+                a0 += rscale * r0;
+                a1 += rscale * r1;
+            }
+            if (MODE == MODE_ADJ) {
+                const double2 wv = ldg2(p.w + gi);
+                part -= wv.x * a0 + wv.y * a1;
+            } else {
+                double2 o;
+                if (MODE == MODE_FIRST) {
+                    const uint64_t s = p.rank_off | gi;
+                    const double d0 = p.no_diag ? 0.0 : tfim_diag_dev(s, p.N, nmask);
+                    const double d1 = p.no_diag ? 0.0 : tfim_diag_dev(s | 1ull, p.N, nmask);
+                    o.x = (d0 - shift) * x[j].x - g * a0;
+                    o.y = (d1 - shift) * x[j].y - g * a1;
+                } else {
+                    o.x = ui[j].x - g * a0;
+                    o.y = ui[j].y - g * a1;
+                }
+                stg2(p.uout + gi, o);
+                if (p.w) {
+                    const double2 wv = (p.w == p.v) ? x[j] : ldg2(p.w + gi);
+                    part += wv.x * o.x + wv.y * o.y;
+                }
+            }
+        }
+        __syncthreads();          // everyone is done with `buf` before the next prefetch overwrites it
+    }
+    if (p.partials) {
+        const double tot = block_sum(part, red);
+        if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
+    }
+}
+
 // Sweep schedule for L local bits with tiles of at most Tmax bits.
 static int plan_sweeps(int L, int Tmax, int run_bits, Sweep* out) {
     int n = 0;
@@ -168,7 +301,20 @@ static int plan_sweeps(int L, int Tmax, int run_bits, Sweep* out) {
 }
 
 template <int MODE>
-static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream_t st) {
+static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, bool pipe, cudaStream_t st) {
+    if (pipe) {
+        const size_t smem2 = (sizeof(double) << kPipeT) * 2;
+        static bool pipe_attr_done[3] = {false, false, false};
+        if (!pipe_attr_done[MODE]) {
+            DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem2));
+            pipe_attr_done[MODE] = true;
+        }
+        tfim_sweep_pipe_kernel<MODE><<<grid, kPipeThreads, smem2, st>>>(p);
+        count_launch(ctx);
+        DSEA_CUDA(cudaGetLastError());
+        return DSEA_OK;
+    }
     const size_t smem = sizeof(double) << p.T;
     static bool attr_done[3] = {false, false, false};
     if (!attr_done[MODE]) {
@@ -236,19 +382,23 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.hshift = sw[j].hshift;
         p.b0 = sw[j].b0;
         p.ntiles = 1ull << (L - sw[j].T);
-        int grid = (int)(p.ntiles < 2048 ? p.ntiles : 2048);
+        // full 2^13 tiles take the persistent double-buffered kernel (one CTA per SM)
+        // (the adjoint reduction keeps the 2-CTA/SM generic kernel: it has no output stream to overlap)
+        const bool pipe = ctx->tfim_pipeline && !mode_adj && p.T == kPipeT && p.c <= 10 && p.ntiles >= 2;
+        int grid = pipe ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
+                        : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
         if (mode_adj) {
             p.w = w;
             p.partials = ctx->partials + total_partials;   // every sweep contributes partial sums
             total_partials += grid;
-            DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, st));
+            DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, pipe, st));
         } else {
             p.w = (last && want_dot) ? w : nullptr;
             p.partials = (last && want_dot) ? ctx->partials : nullptr;
             if (last && want_dot) total_partials = grid;
-            if (j == 0) DSEA_TRY(launch_sweep<MODE_FIRST>(ctx, p, grid, st));
-            else DSEA_TRY(launch_sweep<MODE_ACCUM>(ctx, p, grid, st));
+            if (j == 0) DSEA_TRY(launch_sweep<MODE_FIRST>(ctx, p, grid, pipe, st));
+            else DSEA_TRY(launch_sweep<MODE_ACCUM>(ctx, p, grid, pipe, st));
         }
     }
     prof_end(ctx, tok, st);
