@@ -194,6 +194,8 @@ int dsea_ctx_create(int device, int rank, int world, const void* nccl_id_host, d
     DSEA_CUDA(cudaMallocHost(&ctx->pinned, 64 * sizeof(double)));
     int s = comm_init(ctx, nccl_id_host);
     if (s != DSEA_OK) return s;
+    s = mailbox_setup(ctx);
+    if (s != DSEA_OK) return s;
     *out = ctx;
     return DSEA_OK;
 }
@@ -258,6 +260,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (int)value;
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
+    else if (!strcmp(key, "mailbox")) { if (value == 0) ctx->mail_ok = false; }
     else {
         set_error("unknown option %s", key);
         return DSEA_ERR_ARG;

@@ -54,8 +54,7 @@ int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out,
     dot_kernel<<<grid, kThreads, 0, st>>>(a, b, n, ctx->partials);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    DSEA_TRY(finalize_partials(ctx, grid, 1, out, st));
-    return allreduce_sum(ctx, out, 1, st);
+    return finalize_reduce(ctx, grid, 1, out, st);
 }
 
 // ---- y = a x + b y -------------------------------------------------------------------------------

@@ -139,8 +139,7 @@ int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double*
     cg_init_kernel<<<grid, kCgThreads, 0, st>>>(b, Ax, r, d, n, ctx->partials);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    DSEA_TRY(finalize_partials(ctx, grid, 1, ctx->scal + S_RR, st));
-    DSEA_TRY(allreduce_sum(ctx, ctx->scal + S_RR, 1, st));
+    DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR, st));
     cg_first_check_kernel<<<1, 1, 0, st>>>(ctx->scal);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -155,8 +154,7 @@ int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const 
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    DSEA_TRY(finalize_partials(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
-    DSEA_TRY(allreduce_sum(ctx, ctx->scal + S_RR_NEW, 1, st));
+    DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
     cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal);
     tok = prof_begin(ctx, PK_CG_UPDATE, 24.0 * (double)n, st);
     cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal);

@@ -91,8 +91,11 @@ int comm_init(dsea_ctx* ctx, const void* id128) {
     return DSEA_OK;
 }
 
+static void mailbox_teardown(dsea_ctx* ctx);
+
 int comm_destroy(dsea_ctx* ctx) {
     p2p_teardown(ctx);
+    mailbox_teardown(ctx);
     if (ctx->ipc_scratch) cudaFree(ctx->ipc_scratch);
     ctx->ipc_scratch = nullptr;
     if (ctx->nccl_comm && ctx->nccl) {
@@ -102,8 +105,89 @@ int comm_destroy(dsea_ctx* ctx) {
     return DSEA_OK;
 }
 
+// ---- small all-reduce over peer memory ---------------------------------------------------------------
+// Every reduction in the Lanczos / CG loops is a handful of doubles (<= k).  Instead of a finalize kernel
+// followed by an NCCL all-reduce, ONE kernel sums the per-CTA partials, stores the rank's value straight
+// into every peer's mailbox over NVLink (value, then sequence number with release semantics), waits for
+// the peers' values (acquire) and adds them in rank order — so every rank obtains bit-identical sums,
+// and the call also acts as a barrier.  Two mailbox parities make back-to-back calls safe: a rank can
+// only reach call s+2 after every peer has consumed call s (their value for s+1 is sent afterwards).
+struct MailSlot {
+    double val;
+    unsigned long long seq;
+};
+struct MailParams {
+    MailSlot* peer[kMaxMailRanks];
+    const MailSlot* mine;
+    int world, rank;
+    unsigned long long seq;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(128)
+finalize_allreduce_kernel(const double* __restrict__ partials, int nblocks, int ncols, double* __restrict__ out,
+                          const MailParams mp) {
+    __shared__ double red[32];
+    __shared__ double vals[kMaxMailRanks];
+    const int col = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[(size_t)b * ncols + col];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) vals[mp.rank] = s;
+    __syncthreads();
+    const int par = (int)(mp.seq & 1ull);
+    const int t = threadIdx.x;
+    if (t < mp.world && t != mp.rank) {
+        MailSlot* dst = mp.peer[t] + ((size_t)(mp.rank * 2 + par) * kMaxK + col);
+        dst->val = vals[mp.rank];
+        st_release_sys(&dst->seq, mp.seq);
+        const MailSlot* src = mp.mine + ((size_t)(t * 2 + par) * kMaxK + col);
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(&src->seq) != mp.seq) {
+            if (clock64() - t0 > 240000000000ll) { ok = false; break; }     // ~2 min: a peer died; do not hang the GPU
+        }
+        vals[t] = ok ? *reinterpret_cast<const volatile double*>(&src->val) : __longlong_as_double(0x7ff8000000000000ll);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int r = 0; r < mp.world; ++r) tot += vals[r];
+        out[col] = tot;
+    }
+}
+
+static int mail_launch(dsea_ctx* ctx, const double* partials, int nblocks, int ncols, double* out, cudaStream_t st) {
+    MailParams mp;
+    for (int r = 0; r < kMaxMailRanks; ++r) mp.peer[r] = (MailSlot*)ctx->mail_peer[r];
+    mp.mine = (const MailSlot*)ctx->mail_local;
+    mp.world = ctx->world;
+    mp.rank = ctx->rank;
+    mp.seq = ++ctx->mail_seq;
+    finalize_allreduce_kernel<<<ncols, 128, 0, st>>>(partials, nblocks, ncols, out, mp);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    ctx->fresh_collective = true;
+    return DSEA_OK;
+}
+
+int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st) {
+    if (ctx->world > 1 && ctx->mail_ok && ncols <= kMaxK) return mail_launch(ctx, ctx->partials, nblocks, ncols, out, st);
+    DSEA_TRY(finalize_partials(ctx, nblocks, ncols, out, st));
+    return allreduce_sum(ctx, out, ncols, st);
+}
+
 int allreduce_sum(dsea_ctx* ctx, double* buf, int64_t count, cudaStream_t st) {
     if (ctx->world == 1) return DSEA_OK;
+    if (ctx->mail_ok && count <= kMaxK) return mail_launch(ctx, buf, 1, (int)count, buf, st);
     NcclApi* api = ctx->nccl;
     DSEA_NCCL(api, api->AllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm, st));
     ctx->fresh_collective = true;
@@ -111,7 +195,86 @@ int allreduce_sum(dsea_ctx* ctx, double* buf, int64_t count, cudaStream_t st) {
 }
 
 // A 1-double allreduce used purely as a cross-rank, stream-ordered barrier.
-int comm_barrier(dsea_ctx* ctx, cudaStream_t st) { return allreduce_sum(ctx, ctx->scal + S_TMP1, 1, st); }
+int comm_barrier(dsea_ctx* ctx, cudaStream_t st) {
+    if (ctx->world == 1) return DSEA_OK;
+    DSEA_CUDA(cudaMemsetAsync(ctx->scal + S_TMP1, 0, sizeof(double), st));
+    return allreduce_sum(ctx, ctx->scal + S_TMP1, 1, st);
+}
+
+// Maps every peer's mailbox (collective; called once when the context is created).
+int mailbox_setup(dsea_ctx* ctx) {
+    if (ctx->world == 1 || ctx->world > kMaxMailRanks || ctx->mail_disabled) return DSEA_OK;
+    NcclApi* api = ctx->nccl;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    cudaStream_t st = ctx->comm_stream;
+    const size_t bytes = (size_t)ctx->world * 2 * kMaxK * sizeof(MailSlot);
+    double ok = 1.0;
+    if (cudaMalloc(&ctx->mail_local, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->mail_local = nullptr;
+        ok = 0.0;
+    } else {
+        DSEA_CUDA(cudaMemset(ctx->mail_local, 0, bytes));
+    }
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (ok != 0.0 && cudaIpcGetMemHandle(&mine, ctx->mail_local) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0.0;
+    }
+    if (!ctx->ipc_scratch) DSEA_CUDA(cudaMalloc(&ctx->ipc_scratch, 64 * 256));
+    char* dbuf = (char*)ctx->ipc_scratch;
+    DSEA_CUDA(cudaMemcpyAsync(dbuf + 64 * ctx->rank, &mine, 64, cudaMemcpyHostToDevice, st));
+    DSEA_NCCL(api, api->AllGather(dbuf + 64 * ctx->rank, dbuf, 64, ncclChar, comm, st));
+    cudaIpcMemHandle_t all[256];
+    DSEA_CUDA(cudaMemcpyAsync(all, dbuf, 64 * (size_t)ctx->world, cudaMemcpyDeviceToHost, st));
+    DSEA_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < ctx->world && ok != 0.0; ++r) {
+        if (r == ctx->rank) continue;
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0.0;
+            break;
+        }
+        ctx->mail_peer[r] = base;
+    }
+    double* flag = ctx->scal + S_TMP1;
+    DSEA_CUDA(cudaMemcpyAsync(flag, &ok, sizeof(double), cudaMemcpyHostToDevice, st));
+    DSEA_NCCL(api, api->AllReduce(flag, flag, 1, ncclDouble, ncclMin, comm, st));
+    double agreed = 0.0;
+    DSEA_CUDA(cudaMemcpyAsync(&agreed, flag, sizeof(double), cudaMemcpyDeviceToHost, st));
+    DSEA_CUDA(cudaStreamSynchronize(st));
+    ctx->mail_ok = (agreed != 0.0);
+    ctx->mail_seq = 0;
+    if (!ctx->mail_ok) {
+        for (int r = 0; r < kMaxMailRanks; ++r) {
+            if (ctx->mail_peer[r]) cudaIpcCloseMemHandle(ctx->mail_peer[r]);
+            ctx->mail_peer[r] = nullptr;
+        }
+        if (ctx->mail_local) cudaFree(ctx->mail_local);
+        ctx->mail_local = nullptr;
+    }
+    return DSEA_OK;
+}
+
+static void mailbox_teardown(dsea_ctx* ctx) {
+    if (!ctx->mail_local) return;
+    cudaDeviceSynchronize();
+    NcclApi* api = ctx->nccl;
+    ctx->mail_ok = false;                      // the closing barrier below goes through NCCL
+    for (int r = 0; r < kMaxMailRanks; ++r) {
+        if (ctx->mail_peer[r]) cudaIpcCloseMemHandle(ctx->mail_peer[r]);
+        ctx->mail_peer[r] = nullptr;
+    }
+    if (api && ctx->nccl_comm) {
+        api->AllReduce(ctx->scal + S_TMP1, ctx->scal + S_TMP1, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl_comm,
+                       ctx->comm_stream);
+        cudaStreamSynchronize(ctx->comm_stream);
+    }
+    cudaFree(ctx->mail_local);
+    ctx->mail_local = nullptr;
+}
 
 // ---- peer-memory arena ---------------------------------------------------------------------------
 // Every rank cudaMalloc's an arena of log2(world) slots, publishes its cudaIpcMemHandle with an NCCL

@@ -37,6 +37,7 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 constexpr int kMaxRemote = 8;        // log2(max world) remote (top) spin bits
+constexpr int kMaxMailRanks = 32;    // peer-memory small all-reduce is used up to this many ranks
 constexpr int kMaxSweeps = 8;
 constexpr int kMaxPartialBlocks = 4096;   // upper bound on CTAs writing reduction partials
 constexpr int kMaxK = 2048;               // max Lanczos vectors
@@ -108,6 +109,12 @@ struct dsea_ctx {
     bool p2p_ok = false;
     bool p2p_disabled = false;
     bool fresh_collective = true;       // a collective completed since the arena was last read (WAR guard)
+    // Mailbox for small all-reduces over peer memory (every rank maps every other rank's mailbox).
+    void* mail_local = nullptr;
+    void* mail_peer[dsea::kMaxMailRanks] = {};
+    bool mail_ok = false;
+    bool mail_disabled = false;
+    unsigned long long mail_seq = 0;
     // options
     int tfim_tile_bits = 13;
     int tfim_run_bits = 0;              // 0 = auto
@@ -165,6 +172,8 @@ int axpby(dsea_ctx* ctx, int64_t n, const double* a, const double* x, const doub
 int project(dsea_ctx* ctx, int64_t n, const double* psi, const double* b, double* out, cudaStream_t st);
 int randn(dsea_ctx* ctx, int64_t n, uint64_t seed, uint64_t sid, uint64_t offset, double* out, cudaStream_t st);
 int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st);
+// second reduction stage + cross-rank sum in one step (fused peer-memory kernel when available)
+int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st);   // comm.cu
 // tridiag.cu
 int tridiag_extreme(dsea_ctx* ctx, int k, int which, const double* alpha, const double* beta, const double* keff,
                     double* evals, double* y_min, double* y_max, cudaStream_t st);
@@ -178,6 +187,7 @@ int comm_destroy(dsea_ctx* ctx);
 int comm_unique_id(void* id128);
 int allreduce_sum(dsea_ctx* ctx, double* buf, int64_t count, cudaStream_t st);
 int exchange_shards(dsea_ctx* ctx, const double* send, double* recv_base, int64_t n_loc, cudaStream_t st);
+int mailbox_setup(dsea_ctx* ctx);                 // collective, at context creation
 int p2p_setup(dsea_ctx* ctx, int64_t n_loc);      // collective; falls back to NCCL send/recv if IPC is unavailable
 int p2p_teardown(dsea_ctx* ctx);
 int comm_barrier(dsea_ctx* ctx, cudaStream_t st);

@@ -227,8 +227,7 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    DSEA_TRY(finalize_partials(ctx, grid, m, c_out, st));
-    return allreduce_sum(ctx, c_out, m, st);
+    return finalize_reduce(ctx, grid, m, c_out, st);
 }
 
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, const double* c,
@@ -245,8 +244,7 @@ int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q,
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (norm2_out) {
-        DSEA_TRY(finalize_partials(ctx, grid, 1, norm2_out, st));
-        DSEA_TRY(allreduce_sum(ctx, norm2_out, 1, st));
+        DSEA_TRY(finalize_reduce(ctx, grid, 1, norm2_out, st));
     }
     return DSEA_OK;
 }

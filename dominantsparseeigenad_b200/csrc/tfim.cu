@@ -404,8 +404,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
     prof_end(ctx, tok, st);
     if (p2p) ctx->fresh_collective = false;    // the arena was just read: the next push needs a collective first
     if (want_dot) {
-        DSEA_TRY(finalize_partials(ctx, total_partials, 1, dot_out, st));
-        DSEA_TRY(allreduce_sum(ctx, dot_out, 1, st));
+        DSEA_TRY(finalize_reduce(ctx, total_partials, 1, dot_out, st));
     }
     return DSEA_OK;
 }
