@@ -293,6 +293,34 @@ class TFIM(NativeOperator):
         out = _TFIMAdjoint.apply(self, v1, v2)
         return out if param is None else out.reshape(param.shape)
 
+    # ---- dense builders used by the reference's cross-checks (small N only) ----
+    def setHmatrix(self):
+        """Dense H as a torch.Tensor in `self.Hmatrix`, differentiable in `self.g` (TFIM.py:67-89).
+
+        Built from the same bit arithmetic as the kernels; like the reference it adds a symmetric 1e-12
+        noise so that torch's full-spectrum AD does not divide by zero on exact degeneracies."""
+        if self.rt.world != 1:
+            raise RuntimeError("setHmatrix is a single-GPU, small-N cross-check")
+        n, dev = self.dim, self.device
+        s = torch.arange(n, device=dev)
+        diag = torch.tensor([self.diagonal_element(self.N, int(x)) for x in range(n)], dtype=F64, device=dev)
+        off = torch.zeros(n, n, dtype=F64, device=dev)
+        for i in range(self.N):
+            off[s ^ (1 << i), s] = 1.0
+        noise = 1e-12 * torch.randn(n, n, dtype=F64, device=dev)
+        self.Hmatrix = torch.diag(diag) - self.g.to(dev) * off + 0.5 * (noise + noise.T)
+        return self.Hmatrix
+
+    def setpHpg(self):
+        """Dense dH/dg in `self.pHpgmatrix` (TFIM.py:53-56)."""
+        n, dev = self.dim, self.device
+        s = torch.arange(n, device=dev)
+        m = torch.zeros(n, n, dtype=F64, device=dev)
+        for i in range(self.N):
+            m[s ^ (1 << i), s] = -1.0
+        self.pHpgmatrix = m
+        return m
+
     # bit maps, host side (bit-exact contract with TFIM.py:39-51)
     @staticmethod
     def flip_index(N: int, s: int, i: int) -> int:

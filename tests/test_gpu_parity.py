@@ -433,6 +433,39 @@ def test_config2_tfim_N20_k100_vs_analytic_and_upstream(dsea, orc, golden):
     assert rel(chif, achi) < GRAD_RTOL and rel(chif, up["chiFs_N20"][i]) < GRAD_RTOL
 
 
+def test_tfim_four_methods_agree_N8(dsea, orc):
+    """E0.py:94-108 shape: analytic, torch full-spectrum AD, DominantSymeig (dense) and DominantSparseSymeig
+    (matrix-free) give the same E0, dE0/dg and d2E0/dg2; chi_F also matches the perturbation formula
+    (chiF.py:11-24)."""
+    N, k, g = 8, 256, 1.2
+    m = dsea.TFIM(N)
+    m.g = torch.tensor([g], dtype=F64, device="cuda", requires_grad=True)
+    aE0, adE0, ad2E0, achi = orc.tfim_analytic(N, g)
+    # matrix-free
+    dsea.symeig.setDominantSparseSymeig(m.H, m.Hadjoint_to_gadjoint)
+    E0, _ = dsea.symeig.DominantSparseSymeig.apply(m.g, k, m.dim, torch.device("cuda"))
+    dE0, = torch.autograd.grad(E0, m.g, create_graph=True)
+    d2E0, = torch.autograd.grad(dE0, m.g)
+    # dense primitive and torch's own full-spectrum AD on the same (device-built) matrix
+    Hm = m.setHmatrix()
+    assert (Hm.detach().cpu() - orc.TFIMOracle(N, g).dense()).abs().max().item() < 1e-10
+    E0m, _ = dsea.symeig.DominantSymeig.apply(Hm, k, torch.device("cuda"))
+    dE0m, = torch.autograd.grad(E0m, m.g, create_graph=True)
+    d2E0m, = torch.autograd.grad(dE0m, m.g)
+    Es, psis = torch.linalg.eigh(m.setHmatrix())
+    dE0t, = torch.autograd.grad(Es[0], m.g, create_graph=True)
+    d2E0t, = torch.autograd.grad(dE0t, m.g)
+    for got in ((E0, dE0, d2E0), (E0m, dE0m, d2E0m), (Es[0], dE0t, d2E0t)):
+        assert rel(got[0].item(), aE0) < EVAL_RTOL
+        assert rel(got[1].item(), adE0) < GRAD_RTOL
+        assert rel(got[2].item(), ad2E0) < 1e-5          # the dense variants carry the reference's 1e-12 noise
+    # chi_F by the full-spectrum perturbation formula
+    P = m.setpHpg()
+    num = (psis[:, 0].detach() @ P @ psis.detach())[1:] ** 2
+    chi_pert = (num / (Es[0] - Es[1:]).detach() ** 2).sum().item()
+    assert rel(chi_pert, achi) < 1e-6 and rel(_tfim_chif(dsea, N, g, k), achi) < GRAD_RTOL
+
+
 def test_eigenvector_residual_N18(dsea):
     """|H psi0 - E0 psi0| small and E0 matches the analytic value where no CPU oracle is cheap."""
     from oracle import dsea_oracle as orc
