@@ -312,6 +312,9 @@ def main():
         p = prof[name]
         if p["launches"] == 0 or p["ms"] <= 0:
             return None
+        if p["bytes"] <= 0:          # conditional (normally no-op) launches: report their time share only
+            return {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms"] / args.steps,
+                    "share_of_step": p["ms"] / ms_total}
         gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
         return {"achieved": gbs, "frac": gbs / peak, "launches_per_step": p["launches"] / args.steps,
                 "ms_per_step": p["ms"] / args.steps, "share_of_step": p["ms"] / ms_total,

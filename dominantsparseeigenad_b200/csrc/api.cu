@@ -73,10 +73,28 @@ __global__ void lanczos_reset_kernel(double* scal) {
     scal[S_BREAK] = 0.0;
 }
 
-// alpha[i] = c[i]; beta[i] = sqrt(beta2); flag breakdown (|r| == 0 or not finite) once.
-__global__ void lanczos_record_kernel(double* scal, const double* c, double* alpha, double* beta, int i, int has_beta) {
-    alpha[i] = c[i];
+// Decides on the device whether the Gram-Schmidt sweep lost too many digits: |r| < eta |u| with
+// |u|^2 = |r|^2 + |c|^2 (Q orthonormal).  One sweep leaves an orthogonality error of eps |u| / |r|, so only
+// steps with severe cancellation (Krylov space nearly exhausted, e.g. k >= number of distinct eigenvalues,
+// as in the reference's N=10, k=300 example) are repeated ("twice is enough"); ordinary steps never are.
+__global__ void __launch_bounds__(128) reorth_check_kernel(double* scal, const double* __restrict__ c, int m, double eta2) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int j = threadIdx.x; j < m; j += blockDim.x) s += c[j] * c[j];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        const double b2 = scal[S_BETA2];
+        scal[S_REDO] = (b2 > 0.0 && b2 < eta2 * (b2 + s)) ? 1.0 : 0.0;
+    }
+}
+
+// alpha[i] = c[i] (+ second-sweep correction); beta[i] = sqrt(beta2); flag breakdown (|r| == 0 or not finite) once.
+__global__ void lanczos_record_kernel(double* scal, const double* c, const double* c2, double* alpha, double* beta,
+                                      int i, int has_beta) {
+    const bool redo = has_beta && scal[S_REDO] != 0.0;
+    alpha[i] = c[i] + (redo ? c2[i] : 0.0);
     if (has_beta) {
+        if (redo) scal[S_BETA2] = scal[S_BETA2B];
         const double b2 = scal[S_BETA2];
         const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
         beta[i] = b;
@@ -111,8 +129,19 @@ static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i
         PeerPtrs pp = peer_ptrs(ctx);
         DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, u, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st,
                                push_next ? &pp : nullptr));                                               // :61,66,69
+        // conditional second sweep (device-side decision, no host sync): r -= Q (Q^T r)
+        reorth_check_kernel<<<1, 128, 0, st>>>(ctx->scal, ctx->cvec, m, 1e-6);
+        count_launch(ctx);
+        DSEA_CUDA(cudaGetLastError());
+        ctx->run_flag = ctx->scal + S_REDO;
+        int s2 = reorth_dots(ctx, n, ldq, m, Q, qnext, ctx->yvec, st);
+        if (s2 == DSEA_OK)
+            s2 = reorth_update(ctx, n, ldq, m, Q, qnext, ctx->yvec, -1.0, qnext, ctx->scal + S_BETA2B, st,
+                               push_next ? &pp : nullptr);
+        ctx->run_flag = nullptr;
+        DSEA_TRY(s2);
     }
-    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, ctx->cvec, alpha, beta, i, more ? 1 : 0);
+    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, ctx->cvec, ctx->yvec, alpha, beta, i, more ? 1 : 0);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (more) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));        // :70,75

@@ -62,6 +62,8 @@ enum ScalarSlot {
     S_MAXIT,          // CG: iteration cap
     S_TMP0,
     S_TMP1,
+    S_REDO,           // Lanczos: 1.0 when this step needs a second Gram-Schmidt sweep (severe cancellation)
+    S_BETA2B,         // Lanczos: |r|^2 after the second sweep
     S_COUNT = 32
 };
 
@@ -75,7 +77,7 @@ struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
 struct Profiler;  // optional per-kernel CUDA-event timing (api.cu)
 
 enum ProfKind { PK_MATVEC = 0, PK_REORTH_DOTS, PK_REORTH_UPDATE, PK_RITZ, PK_CG_UPDATE, PK_NORMALISE, PK_TRIDIAG,
-                PK_ADJOINT, PK_COUNT };
+                PK_ADJOINT, PK_REORTH_REDO, PK_COUNT };
 
 }  // namespace dsea
 
@@ -98,6 +100,7 @@ struct dsea_ctx {
     unsigned int* counters = nullptr;   // device counters (last-block patterns)
     int64_t launches = 0;
     const double* guard = nullptr;      // device flag consulted by operator kernels (set during CG)
+    const double* run_flag = nullptr;   // when set, reorth / reduction kernels run only if *run_flag != 0
     dsea::Profiler* prof = nullptr;     // non-null while per-kernel timing is enabled
     // Peer-memory exchange arena (CUDA IPC over NVLink): slot j receives the shard of rank ^ (1 << j),
     // written there directly by the PRODUCING kernel of that rank (fused compute + exchange).

@@ -58,8 +58,9 @@ __device__ __forceinline__ double warp_reduce8(double (&v)[8], int lane) {
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
-                   double* __restrict__ partials) {
+                   double* __restrict__ partials, const double* __restrict__ run_flag) {
     extern __shared__ double wacc[];                 // [8 warps][m] per-warp accumulators
+    if (run_flag && *run_flag == 0.0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = threadIdx.x; j < 8 * m; j += kRThreads) wacc[j] = 0.0;
     __syncthreads();
@@ -124,9 +125,10 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
                      const double* __restrict__ c, double sign, int64_t n, int m, double* __restrict__ r,
-                     double* __restrict__ partials, const PeerPtrs peers) {
+                     double* __restrict__ partials, const PeerPtrs peers, const double* __restrict__ run_flag) {
     extern __shared__ double cs[];                   // m coefficients (pre-multiplied by sign)
     __shared__ double red[32];
+    if (run_flag && *run_flag == 0.0) return;
     for (int j = threadIdx.x; j < m; j += kRThreads) cs[j] = sign * c[j];
     __syncthreads();
     const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
@@ -222,8 +224,9 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
         DSEA_CUDA(cudaFuncSetAttribute(reorth_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_set = 200 * 1024;
     }
-    const int tok = prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1), st);
-    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials);
+    const int tok = ctx->run_flag ? prof_begin(ctx, PK_REORTH_REDO, 0.0, st)
+                                  : prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1), st);
+    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, ctx->run_flag);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -234,12 +237,13 @@ int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q,
                   double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
     const int grid = reorth_grid(ctx, n);
     const size_t smem = (size_t)m * sizeof(double);
-    const int tok = prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
+    const int tok = ctx->run_flag ? prof_begin(ctx, PK_REORTH_REDO, 0.0, st)
+                                  : prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
     reorth_update_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
-                                                       norm2_out ? ctx->partials : nullptr, pp);
+                                                       norm2_out ? ctx->partials : nullptr, pp, ctx->run_flag);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());

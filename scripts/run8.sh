@@ -12,7 +12,7 @@ name=sys.argv[1]
 try:
     d=json.loads(open(f"gpurun_out/{name}.json").read().strip().splitlines()[-1])
     print(name, d["config"]["workload"], "value", round(d["value"],4), "e2e", round(d["e2e"]["value"],4), d["analytic_check"], d["clocks"],
-          {k:(round(v["ms_per_step"],1), round(v["frac"],3)) for k,v in d["kernels"].items()}, "cg", d["cg_iterations_per_solve"][:3])
+          {k:(round(v["ms_per_step"],1), round(v.get("frac",0),3)) for k,v in d["kernels"].items()}, "cg", d["cg_iterations_per_solve"][:3])
 except Exception as e:
     print(name, "FAILED", e, open(f"gpurun_out/{name}.json").read()[-1500:])
 PY
