@@ -73,31 +73,14 @@ __global__ void lanczos_reset_kernel(double* scal) {
     scal[S_BREAK] = 0.0;
 }
 
-// Decides on the device whether the Gram-Schmidt sweep lost too many digits: |r| < eta |u| with
-// |u|^2 = |r|^2 + |c|^2 (Q orthonormal).  One sweep leaves an orthogonality error of eps |u| / |r|, so only
-// steps with severe cancellation (Krylov space nearly exhausted, e.g. k >= number of distinct eigenvalues,
-// as in the reference's N=10, k=300 example) are repeated ("twice is enough"); ordinary steps never are.
-__global__ void __launch_bounds__(128) reorth_check_kernel(double* scal, const double* __restrict__ c, int m, double eta2) {
-    __shared__ double red[32];
-    double s = 0.0;
-    for (int j = threadIdx.x; j < m; j += blockDim.x) s += c[j] * c[j];
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) {
-        const double b2 = scal[S_BETA2];
-        scal[S_REDO] = (b2 > 0.0 && b2 < eta2 * (b2 + s)) ? 1.0 : 0.0;
-    }
-}
-
-// alpha[i] = c[i] (+ second-sweep correction); beta[i] = sqrt(beta2); flag breakdown (|r| == 0 or not finite) once.
-__global__ void lanczos_record_kernel(double* scal, const double* c, const double* c2, double* alpha, double* beta,
-                                      int i, int has_beta) {
-    const bool redo = has_beta && scal[S_REDO] != 0.0;
-    alpha[i] = c[i] + (redo ? c2[i] : 0.0);
+// alpha[i] = q_i . A q_i (Lanczos.py:55,72); beta[i] = |r| after re-orthogonalisation (:69); flags breakdown once.
+__global__ void lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_beta) {
+    alpha[i] = scal[S_ALPHA_L];
     if (has_beta) {
-        if (redo) scal[S_BETA2] = scal[S_BETA2B];
         const double b2 = scal[S_BETA2];
         const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
         beta[i] = b;
+        scal[S_BETAPREV] = b;
         scal[S_INVBETA] = (b > 0.0 && isfinite(b)) ? 1.0 / b : 0.0;
         if (!(b > 0.0) || !isfinite(b)) {
             if (scal[S_BREAK] == 0.0) {
@@ -117,31 +100,36 @@ static int lanczos_start_impl(dsea_ctx* ctx, int64_t n, double* Q, cudaStream_t 
     return scale_by_inv_sqrt(ctx, n, Q, ctx->scal + S_BETA2, st);          // Lanczos.py:53
 }
 
+// One Lanczos step exactly as the reference orders it (Lanczos.py:61-75):
+//   r0 = u - alpha_i q_i - beta_{i-1} q_{i-1}      (formed in the prologue of pass 1, written to Q[:, i+1])
+//   c  = Q[:, :i+1]^T r0 ; r = r0 - Q[:, :i+1] c    (one classical Gram-Schmidt sweep, two fused passes)
+//   beta_i = |r| ; q_{i+1} = r / beta_i
+// Removing the two large components with the recurrence scalars BEFORE the sweep is what keeps the
+// orthogonality defect from being re-amplified by |alpha| / beta every step (a sweep applied to u
+// itself is unstable once beta becomes small, e.g. for k close to the Krylov dimension).
+// `alpha_ready`: scal[S_ALPHA_L] already holds q_i . u (epilogue of the matvec); otherwise it is computed here.
 // `push_next`: pass 2 also stores the new (un-normalised) vector into the partners' arenas, so the next
-// matvec finds its remote shards already in place (the beta^2 allreduce that follows is the barrier).
+// matvec finds its remote shards already in place (the beta^2 reduction that follows is the barrier).
 static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i, double* Q, const double* u,
-                             double* alpha, double* beta, cudaStream_t st, bool push_next = false) {
+                             double* alpha, double* beta, cudaStream_t st, bool alpha_ready, bool push_next = false) {
     const int m = i + 1;
-    DSEA_TRY(reorth_dots(ctx, n, ldq, m, Q, u, ctx->cvec, st));                       // c = Q^T u; alpha_i = c_i
+    const double* qi = Q + (int64_t)i * ldq;
+    if (!alpha_ready) DSEA_TRY(dot(ctx, n, qi, u, ctx->scal + S_ALPHA_L, st));
     const bool more = (i < k - 1);
     if (more) {
         double* qnext = Q + (int64_t)m * ldq;
+        Recurrence rec;
+        rec.qi = qi;
+        rec.qim1 = i > 0 ? Q + (int64_t)(i - 1) * ldq : nullptr;
+        rec.alpha = ctx->scal + S_ALPHA_L;
+        rec.beta = ctx->scal + S_BETAPREV;
+        rec.r0_out = qnext;
+        DSEA_TRY(reorth_dots(ctx, n, ldq, m, Q, u, ctx->cvec, st, &rec));
         PeerPtrs pp = peer_ptrs(ctx);
-        DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, u, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st,
-                               push_next ? &pp : nullptr));                                               // :61,66,69
-        // conditional second sweep (device-side decision, no host sync): r -= Q (Q^T r)
-        reorth_check_kernel<<<1, 128, 0, st>>>(ctx->scal, ctx->cvec, m, 1e-6);
-        count_launch(ctx);
-        DSEA_CUDA(cudaGetLastError());
-        ctx->run_flag = ctx->scal + S_REDO;
-        int s2 = reorth_dots(ctx, n, ldq, m, Q, qnext, ctx->yvec, st);
-        if (s2 == DSEA_OK)
-            s2 = reorth_update(ctx, n, ldq, m, Q, qnext, ctx->yvec, -1.0, qnext, ctx->scal + S_BETA2B, st,
-                               push_next ? &pp : nullptr);
-        ctx->run_flag = nullptr;
-        DSEA_TRY(s2);
+        DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, qnext, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st,
+                               push_next ? &pp : nullptr));
     }
-    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, ctx->cvec, ctx->yvec, alpha, beta, i, more ? 1 : 0);
+    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, alpha, beta, i, more ? 1 : 0);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (more) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));        // :70,75
@@ -411,9 +399,9 @@ int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, i
     const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->p2p_ok && ctx->arena_stride >= n;
     for (int i = 0; i < k; ++i) {
         const bool pre = fuse_push && i > 0;
-        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, nullptr, opwork, st, pre,
-                          ctx->scal + S_INVBETA));                                                   // Lanczos.py:54,71
-        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, fuse_push));
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, ctx->scal + S_ALPHA_L, opwork, st, pre,
+                          ctx->scal + S_INVBETA));                                  // Lanczos.py:54-55,71-72 (alpha in the epilogue)
+        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, true, fuse_push));
     }
     return lanczos_ritz_impl(ctx, n, ldq, k, which, Q, alpha, beta, evals, evec_min, evec_max, info_host, st);
 }
@@ -428,7 +416,7 @@ int dsea_lanczos_step(dsea_ctx* ctx, int64_t n_loc, int k, int i, double* Q, con
     DSEA_ARG(ctx && Q && u && alpha && beta, "NULL argument");
     DSEA_ARG(i >= 0 && i < k && k <= kMaxK, "step index out of range");
     DSEA_ARG(aligned16(Q) && aligned16(u), "buffers must be 16-byte aligned");
-    return lanczos_step_impl(ctx, n_loc, col_stride(n_loc), k, i, Q, u, alpha, beta, (cudaStream_t)stream);
+    return lanczos_step_impl(ctx, n_loc, col_stride(n_loc), k, i, Q, u, alpha, beta, (cudaStream_t)stream, false);
 }
 
 int dsea_lanczos_ritz(dsea_ctx* ctx, int64_t n_loc, int k, int which, const double* Q, const double* alpha,

@@ -62,8 +62,8 @@ enum ScalarSlot {
     S_MAXIT,          // CG: iteration cap
     S_TMP0,
     S_TMP1,
-    S_REDO,           // Lanczos: 1.0 when this step needs a second Gram-Schmidt sweep (severe cancellation)
-    S_BETA2B,         // Lanczos: |r|^2 after the second sweep
+    S_ALPHA_L,        // Lanczos: alpha_i = q_i . A q_i of the current step
+    S_BETAPREV,       // Lanczos: beta_{i-1}
     S_COUNT = 32
 };
 
@@ -71,6 +71,16 @@ enum ScalarSlot {
 struct PeerPtrs {
     double* p[kMaxRemote];
     int n;
+};
+
+// Three-term recurrence applied in the prologue of reorth pass 1: r0 = u - (*alpha) qi - (*beta) qim1,
+// written to r0_out (qim1 may be NULL for the first step).
+struct Recurrence {
+    const double* qi;
+    const double* qim1;
+    const double* alpha;
+    const double* beta;
+    double* r0_out;
 };
 
 struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
@@ -164,7 +174,7 @@ int hadamard(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double*
 int outer(dsea_ctx* ctx, int64_t n, double scale, const double* a, const double* b, double* out, cudaStream_t st);
 // reorth.cu
 int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u, double* c_out,
-                cudaStream_t st);   // c_out[0..ncols) = Q^T u  (allreduced)
+                cudaStream_t st, const Recurrence* rec = nullptr);   // c_out = Q^T (u [- recurrence terms])  (allreduced)
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u,
                   const double* c, double sign, double* r_out, double* norm2_out,
                   cudaStream_t st, const PeerPtrs* peers = nullptr);   // r = u + sign * Q c  (u may be NULL)

@@ -58,9 +58,12 @@ __device__ __forceinline__ double warp_reduce8(double (&v)[8], int lane) {
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
-                   double* __restrict__ partials, const double* __restrict__ run_flag) {
+                   double* __restrict__ partials, const double* __restrict__ run_flag, const Recurrence rec) {
     extern __shared__ double wacc[];                 // [8 warps][m] per-warp accumulators
     if (run_flag && *run_flag == 0.0) return;
+    // three-term recurrence folded into the prologue: r0 = u - alpha q_i - beta q_{i-1}  (Lanczos.py:61)
+    const double ra = rec.qi ? *rec.alpha : 0.0;
+    const double rb = rec.qim1 ? *rec.beta : 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = threadIdx.x; j < 8 * m; j += kRThreads) wacc[j] = 0.0;
     __syncthreads();
@@ -80,6 +83,28 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
             u0.y = r0 + 1 < n ? u[r0 + 1] : 0.0;
             u1.x = r1 < n ? u[r1] : 0.0;
             u1.y = r1 + 1 < n ? u[r1 + 1] : 0.0;
+        }
+        if (rec.qi) {
+            if (full) {
+                const double2 q0 = ldg2(rec.qi + r0), q1 = ldg2(rec.qi + r1);
+                u0.x -= ra * q0.x; u0.y -= ra * q0.y; u1.x -= ra * q1.x; u1.y -= ra * q1.y;
+                if (rec.qim1) {
+                    const double2 p0 = ldg2(rec.qim1 + r0), p1 = ldg2(rec.qim1 + r1);
+                    u0.x -= rb * p0.x; u0.y -= rb * p0.y; u1.x -= rb * p1.x; u1.y -= rb * p1.y;
+                }
+                stg2(rec.r0_out + r0, u0);
+                stg2(rec.r0_out + r1, u1);
+            } else {
+                const int64_t rows[4] = {r0, r0 + 1, r1, r1 + 1};
+                double* uv[4] = {&u0.x, &u0.y, &u1.x, &u1.y};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rows[q] < n) {
+                        *uv[q] -= ra * rec.qi[rows[q]];
+                        if (rec.qim1) *uv[q] -= rb * rec.qim1[rows[q]];
+                        rec.r0_out[rows[q]] = *uv[q];
+                    }
+            }
         }
         for (int j0 = 0; j0 < m; j0 += kJB) {
             double acc[kJB];
@@ -215,7 +240,7 @@ static inline int reorth_grid(const dsea_ctx* ctx, int64_t n) {
 }
 
 int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, double* c_out,
-                cudaStream_t st) {
+                cudaStream_t st, const Recurrence* rec) {
     const int grid = reorth_grid(ctx, n);
     const size_t smem = (size_t)8 * m * sizeof(double);
     DSEA_ARG(smem <= 200 * 1024, "too many Lanczos vectors for the reorth accumulators");
@@ -225,8 +250,13 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
         smem_set = 200 * 1024;
     }
     const int tok = ctx->run_flag ? prof_begin(ctx, PK_REORTH_REDO, 0.0, st)
-                                  : prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1), st);
-    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, ctx->run_flag);
+                                  : prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1 + (rec ? 3 : 0)), st);
+    Recurrence rc;
+    rc.qi = rc.qim1 = nullptr;
+    rc.alpha = rc.beta = nullptr;
+    rc.r0_out = nullptr;
+    if (rec) rc = *rec;
+    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, ctx->run_flag, rc);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
