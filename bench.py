@@ -323,10 +323,21 @@ def main():
     kernels = {nm: kernel_line(nm) for nm in prof if kernel_line(nm)}
     dom = kernels.get("reorth_update")
     roofline = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")       # from one `ncu --set full` capture
+    if dom and os.path.exists(tpath):
+        try:
+            recs = json.load(open(tpath)).get("dsea::reorth_update_kernel", [])
+            if recs:
+                ratio = sum(r["traffic_over_algorithmic"] for r in recs) / len(recs)
+                traffic = ratio * dom["algorithmic_bytes_per_step"] / dom["launches_per_step"]
+        except Exception:
+            traffic = None
     if dom:
         roofline = {"kernel": "reorth_update_kernel (r = u - Q c, pass 2 of full re-orthogonalisation)",
                     "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "achieved_bytes_per_launch": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"],
                     "bytes_model": "8 n_loc (m + 2) per launch with m stored vectors (read Q[:, :m], read u, write r)",
                     "share_of_step": dom["share_of_step"]}
 
