@@ -327,7 +327,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")       # from one `ncu --set full` capture
     if dom and os.path.exists(tpath):
         try:
-            recs = json.load(open(tpath)).get("dsea::reorth_update_kernel", [])
+            recs = [r for kname, v in json.load(open(tpath)).items() if "reorth_update_kernel" in kname for r in v]
             if recs:
                 ratio = sum(r["traffic_over_algorithmic"] for r in recs) / len(recs)
                 traffic = ratio * dom["algorithmic_bytes_per_step"] / dom["launches_per_step"]

@@ -386,7 +386,8 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         // (the adjoint reduction keeps the 2-CTA/SM generic kernel: it has no output stream to overlap)
         // and so does a sweep that adds remote shards: its extra HBM reads sit in the epilogue, where the
         // 2-CTA/SM kernel hides their latency better — measured 81.7 vs 99.3 ms per solve at P=2)
-        const bool pipe = ctx->tfim_pipeline && !mode_adj && p.nrecv == 0 && p.T == kPipeT && p.c <= 10 && p.ntiles >= 2;
+        const bool pipe = ctx->tfim_pipeline && !mode_adj && p.nrecv == 0 && p.T == kPipeT && (p.b0 == 0 || p.c <= 10) &&
+                          p.ntiles >= 2;
         int grid = pipe ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
                         : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
