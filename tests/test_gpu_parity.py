@@ -576,3 +576,105 @@ def test_dominant_eig_restarts_when_k_is_small(dsea):
     ref = w[torch.argmax(w.abs())]
     assert abs(ref.imag.item()) < 1e-12 and rel(lam.item(), ref.real.item()) < EVAL_RTOL
     assert (A @ r - lam * r).norm().item() < 1e-9 and (A.T @ l - lam * l).norm().item() < 1e-9 * l.norm().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size invariants, edge cases, error behaviour
+# ------------------------------------------------------------------------------------------------
+def test_full_size_invariants_N24(dsea):
+    """BASELINE's single-GPU size (2^24 amplitudes): properties that need no oracle.
+    Ritz pair from k=48 vectors: |psi| = 1, Rayleigh quotient == theta, residual == beta_k |y_k| bound,
+    basis orthonormal on sampled columns, operator symmetric."""
+    N, k, g = 24, 48, 1.0
+    m = dsea.TFIM(N)
+    m.g = cuda([g])
+    gen = torch.Generator(device="cuda").manual_seed(24)
+    v = torch.randn(m.dim, dtype=F64, device="cuda", generator=gen)
+    w = torch.randn(m.dim, dtype=F64, device="cuda", generator=gen)
+    assert rel(torch.dot(w, m.H(v)).item(), torch.dot(m.H(w), v).item()) < 1e-11
+    del v, w
+    evals, psi, _, st = m.lanczos(m.g, k, 0)
+    theta = evals[0].item()
+    assert abs(torch.dot(psi, psi).item() - 1.0) < 1e-12
+    Hpsi = m.H(psi)
+    assert rel(torch.dot(psi, Hpsi).item(), theta) < 1e-12                       # Ritz value = Rayleigh quotient
+    resid = (Hpsi - theta * psi).norm().item()
+    assert resid <= st["beta"][: k - 1].max().item() * 1.0001                    # |r| = beta_k |y_k| <= max beta
+    Q, ldq = st["Q"], st["ldq"]
+    cols = [0, 1, k // 2, k - 2, k - 1]
+    G = torch.stack([Q[j * ldq:j * ldq + m.dim] for j in cols])
+    assert (G @ G.T - torch.eye(len(cols), dtype=F64, device="cuda")).abs().max().item() < 1e-12
+    # upper bound property: theta_min(k) >= E0, and within 1e-3 already at k=48
+    from oracle import dsea_oracle as orc
+    E0 = orc.tfim_analytic(N, g)[0]
+    assert theta >= E0 - 1e-9 and rel(theta, E0) < 1e-3
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_lanczos_tiny_k(dsea, k):
+    torch.manual_seed(k)
+    n = 50
+    A = torch.randn(n, n, dtype=F64, device="cuda")
+    A = A + A.T
+    q0 = torch.randn(n, dtype=F64)
+    dsea.runtime.set_start_vector_hook(lambda nn, kind: q0)
+    try:
+        lo, vlo, hi, vhi = dsea.Lanczos.symeigLanczos(A, k, device=torch.device("cuda"))
+    finally:
+        dsea.runtime.set_start_vector_hook(None)
+    # reference semantics: eigenvalues of the k x k projection onto the Krylov space of q0
+    Qs = [q0.cuda() / q0.norm()]
+    for _ in range(k - 1):
+        r = A @ Qs[-1]
+        for q in Qs:
+            r = r - torch.dot(q, r) * q
+        Qs.append(r / r.norm())
+    Qm = torch.stack(Qs, 1)
+    w = torch.linalg.eigvalsh(Qm.T @ A @ Qm)
+    assert rel(lo.item(), w[0].item()) < 1e-10 and rel(hi.item(), w[-1].item()) < 1e-10
+    assert abs(vlo.norm().item() - 1) < 1e-12
+
+
+def test_csr_operator_ragged_and_dense_rows(dsea):
+    """CSR SpMV: odd dimension, empty rows, short rows (thread-per-row) and long rows (warp-per-row)."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    for n, density in ((777, 0.004), (1001, 0.05)):
+        M = sp.random(n, n, density=density, random_state=rng, format="csr")
+        M = (M + M.T).tocsr()
+        M[5, :] = 0
+        M[:, 5] = 0
+        M.eliminate_zeros()
+        pot = torch.from_numpy(rng.standard_normal(n)).cuda()
+        op = dsea.SparseMatrixOperator.from_scipy(M, pot)
+        v = rng.standard_normal(n)
+        want = M @ v + pot.cpu().numpy() * v
+        got = op.H(torch.from_numpy(v).cuda()).cpu().numpy()
+        assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+        # and through the solver: smallest eigenvalue of M + diag(pot)
+        E0, psi = dsea.Lanczos.symeigLanczos(op.H, min(n, 400), device=torch.device("cuda"), extreme="min",
+                                             sparse=True, dim=n)
+        ref = np.linalg.eigvalsh(M.toarray() + np.diag(pot.cpu().numpy()))[0]
+        assert rel(E0.item(), ref) < 1e-9
+
+
+def test_error_behaviour(dsea):
+    """Bad arguments raise (status + dsea_last_error), they do not crash or fall back."""
+    from dominantsparseeigenad_b200 import _lib
+    rt = dsea.runtime.context()
+    with pytest.raises(_lib.DseaError):
+        dsea.TFIM(1)                                         # too few spins
+    with pytest.raises(_lib.DseaError):
+        dsea.TFIM(64)
+    A = torch.eye(8, dtype=F64, device="cuda")
+    with pytest.raises(_lib.DseaError):
+        dsea.Lanczos.symeigLanczos(A, 5000)                  # k beyond the supported maximum
+    with pytest.raises(ValueError):
+        dsea.Lanczos.symeigLanczos(A, 4, extreme="middle")
+    with pytest.raises(TypeError):
+        dsea.Lanczos.symeigLanczos(lambda v: v, 4)           # callable without sparse=True
+    with pytest.raises(_lib.DseaError):
+        rt.set_option("no_such_option", 1)
+    m = dsea.TFIM(6)
+    with pytest.raises(ValueError):
+        m.H(torch.zeros(64, dtype=F64, device="cuda"))       # g not set
