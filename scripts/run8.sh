@@ -20,5 +20,5 @@ PY
 run bench_P8_N27 8 --steps 3 --warmup 3
 run bench_P4_N26 4 --steps 3 --warmup 3
 run bench_P8_N28_k200 8 --spins 28 --k 200 --steps 3 --warmup 3
-run bench_P4_N28_k200 4 --spins 28 --k 200 --steps 3 --warmup 3
+# (N=28 on 4 GPUs measured earlier in the round: profiles/r1_bench_P4_N28_k200.json)
 run bench_P8_N30_kfit 8 --spins 30 --k 0 --steps 3 --warmup 3
