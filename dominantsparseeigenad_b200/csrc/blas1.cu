@@ -17,9 +17,8 @@ static inline int stream_grid(const dsea_ctx* ctx, int64_t n, int per_thread = 8
 
 // ---- second stage of every reduction: out[col] = sum_b partials[b*ncols + col], fixed order ----
 __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict__ partials, int nblocks, int ncols,
-                                                       double* __restrict__ out, const double* __restrict__ run_flag) {
+                                                       double* __restrict__ out) {
     __shared__ double red[32];
-    if (run_flag && *run_flag == 0.0) return;
     const int col = blockIdx.x;
     double s = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[(size_t)b * ncols + col];
@@ -28,7 +27,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
 }
 
 int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st) {
-    finalize_kernel<<<ncols, 128, 0, st>>>(ctx->partials, nblocks, ncols, out, ctx->run_flag);
+    finalize_kernel<<<ncols, 128, 0, st>>>(ctx->partials, nblocks, ncols, out);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;

@@ -134,10 +134,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __global__ void __launch_bounds__(128)
 finalize_allreduce_kernel(const double* __restrict__ partials, int nblocks, int ncols, double* __restrict__ out,
-                          const MailParams mp, const double* __restrict__ run_flag) {
+                          const MailParams mp) {
     __shared__ double red[32];
     __shared__ double vals[kMaxMailRanks];
-    if (run_flag && *run_flag == 0.0) return;      // replicated flag: every rank skips the same calls
     const int col = blockIdx.x;
     double s = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partials[(size_t)b * ncols + col];
@@ -173,7 +172,7 @@ static int mail_launch(dsea_ctx* ctx, const double* partials, int nblocks, int n
     mp.world = ctx->world;
     mp.rank = ctx->rank;
     mp.seq = ++ctx->mail_seq;
-    finalize_allreduce_kernel<<<ncols, 128, 0, st>>>(partials, nblocks, ncols, out, mp, ctx->run_flag);
+    finalize_allreduce_kernel<<<ncols, 128, 0, st>>>(partials, nblocks, ncols, out, mp);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     ctx->fresh_collective = true;

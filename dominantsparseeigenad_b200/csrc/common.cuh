@@ -87,7 +87,7 @@ struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
 struct Profiler;  // optional per-kernel CUDA-event timing (api.cu)
 
 enum ProfKind { PK_MATVEC = 0, PK_REORTH_DOTS, PK_REORTH_UPDATE, PK_RITZ, PK_CG_UPDATE, PK_NORMALISE, PK_TRIDIAG,
-                PK_ADJOINT, PK_REORTH_REDO, PK_COUNT };
+                PK_ADJOINT, PK_COUNT };
 
 }  // namespace dsea
 
@@ -110,7 +110,6 @@ struct dsea_ctx {
     unsigned int* counters = nullptr;   // device counters (last-block patterns)
     int64_t launches = 0;
     const double* guard = nullptr;      // device flag consulted by operator kernels (set during CG)
-    const double* run_flag = nullptr;   // when set, reorth / reduction kernels run only if *run_flag != 0
     dsea::Profiler* prof = nullptr;     // non-null while per-kernel timing is enabled
     // Peer-memory exchange arena (CUDA IPC over NVLink): slot j receives the shard of rank ^ (1 << j),
     // written there directly by the PRODUCING kernel of that rank (fused compute + exchange).

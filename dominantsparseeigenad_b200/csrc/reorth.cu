@@ -58,9 +58,8 @@ __device__ __forceinline__ double warp_reduce8(double (&v)[8], int lane) {
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
-                   double* __restrict__ partials, const double* __restrict__ run_flag, const Recurrence rec) {
+                   double* __restrict__ partials, const Recurrence rec) {
     extern __shared__ double wacc[];                 // [8 warps][m] per-warp accumulators
-    if (run_flag && *run_flag == 0.0) return;
     // three-term recurrence folded into the prologue: r0 = u - alpha q_i - beta q_{i-1}  (Lanczos.py:61)
     const double ra = rec.qi ? *rec.alpha : 0.0;
     const double rb = rec.qim1 ? *rec.beta : 0.0;
@@ -150,10 +149,9 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
                      const double* __restrict__ c, double sign, int64_t n, int m, double* __restrict__ r,
-                     double* __restrict__ partials, const PeerPtrs peers, const double* __restrict__ run_flag) {
+                     double* __restrict__ partials, const PeerPtrs peers) {
     extern __shared__ double cs[];                   // m coefficients (pre-multiplied by sign)
     __shared__ double red[32];
-    if (run_flag && *run_flag == 0.0) return;
     for (int j = threadIdx.x; j < m; j += kRThreads) cs[j] = sign * c[j];
     __syncthreads();
     const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
@@ -249,14 +247,14 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
         DSEA_CUDA(cudaFuncSetAttribute(reorth_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_set = 200 * 1024;
     }
-    const int tok = ctx->run_flag ? prof_begin(ctx, PK_REORTH_REDO, 0.0, st)
-                                  : prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1 + (rec ? 3 : 0)), st);
+    const int tok =
+        prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1 + (rec ? 3 : 0)), st);
     Recurrence rc;
     rc.qi = rc.qim1 = nullptr;
     rc.alpha = rc.beta = nullptr;
     rc.r0_out = nullptr;
     if (rec) rc = *rec;
-    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, ctx->run_flag, rc);
+    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, rc);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -267,13 +265,13 @@ int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q,
                   double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
     const int grid = reorth_grid(ctx, n);
     const size_t smem = (size_t)m * sizeof(double);
-    const int tok = ctx->run_flag ? prof_begin(ctx, PK_REORTH_REDO, 0.0, st)
-                                  : prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
+    const int tok =
+        prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
     reorth_update_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
-                                                       norm2_out ? ctx->partials : nullptr, pp, ctx->run_flag);
+                                                       norm2_out ? ctx->partials : nullptr, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());

@@ -62,7 +62,7 @@ class Context:
         return int(self.lib.dsea_launch_count(self.handle))
 
     PROFILE_KINDS = ("matvec", "reorth_dots", "reorth_update", "ritz", "cg_update", "normalise", "tridiag",
-                     "adjoint", "reorth_redo")
+                     "adjoint")
 
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self.lib.dsea_profile_enable(self.handle, 1 if on else 0))
