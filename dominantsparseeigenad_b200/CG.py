@@ -71,32 +71,6 @@ def _project_any(psi, v):
     return project(psi, v).to(v.device)
 
 
-def make_cg_subspace_sparse(op, Aadjoint_to_gadjoint=None):
-    """Builds the CGSubspaceSparse Function bound to operator `op` (CG.py:116-140)."""
-
-    class CGSubspaceSparse(torch.autograd.Function):
-        @staticmethod
-        def forward(ctx, g, E0, b, alpha):
-            x = _solve_on_subspace(op, g, E0, b, alpha).to(b.device)
-            ctx.g = g
-            ctx.save_for_backward(E0, alpha, x)
-            return x
-
-        @staticmethod
-        def backward(ctx, grad_x):
-            g = ctx.g
-            E0, alpha, x = ctx.saved_tensors
-            rhs = _project_any(alpha, grad_x)                               # CG.py:132
-            grad_b = CGSubspaceSparse.apply(g, E0, rhs, alpha)              # :133
-            v1, v2 = -grad_b, x                                             # :134
-            grad_alpha = -scale(_dot_any(alpha, grad_x), x)                 # :135
-            grad_E0 = -_dot_any(v1, v2)                                     # :136
-            grad_g = _param_adjoint(op, Aadjoint_to_gadjoint, v1, v2, g)    # :137
-            return grad_g, grad_E0, grad_b, grad_alpha
-
-    return CGSubspaceSparse
-
-
 def _param_adjoint(op, user_adjoint, v1, v2, g):
     if getattr(op, "_dsea_native", False):
         out = op.adjoint(v1, v2, g)
@@ -143,7 +117,7 @@ def setCGSubspaceSparse(A, Aadjoint_to_gadjoint):
             E0, alpha, x = ctx.saved_tensors
             op = _Lazy.get(x)
             rhs = _project_any(alpha, grad_x)
-            grad_b = CGSubspaceSparse.apply(g, E0, rhs, alpha)              # looked up at call time, CG.py:131
+            grad_b = _Dispatch.apply(g, E0, rhs, alpha)        # CG.py:131,133 — bound to THIS operator, not the global
             v1, v2 = -grad_b, x
             grad_alpha = -scale(_dot_any(alpha, grad_x), x)
             grad_E0 = -_dot_any(v1, v2)

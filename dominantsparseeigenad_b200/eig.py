@@ -19,7 +19,6 @@ Conventions follow eig.py:22-24: l^T r = 1 and r^T r = 1; the eigenvalue must be
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Callable
 
 import numpy as np

@@ -16,7 +16,7 @@ import torch
 
 from . import CG as _CG
 from . import _lib
-from .CG import _dot_any, _param_adjoint, _project_any
+from .CG import _param_adjoint, _project_any
 from .operators import as_operator, scale
 
 

@@ -1,6 +1,5 @@
 """CPU: libdsea.so builds/loads and exports exactly the C ABI that include/dsea.h declares; the
 host-callable bit maps are bit-exact against the reference tables.  No GPU compute here."""
-import ctypes
 import os
 import re
 

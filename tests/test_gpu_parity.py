@@ -6,7 +6,6 @@ properties (symmetry, linearity, analytic values).
 Tolerances (BASELINE.json north_star): integer maps bit-exact; eigenvalues 1e-10 relative;
 eigenvector overlap >= 1 - 1e-8; gradients (dE0/dg, d2E0/dg2, chi_F) 1e-6 relative.
 """
-import math
 
 import numpy as np
 import pytest
