@@ -38,7 +38,7 @@ void set_error(const char* fmt, ...);
 
 constexpr int kMaxRemote = 8;        // log2(max world) remote (top) spin bits
 constexpr int kMaxMailRanks = 32;    // peer-memory small all-reduce is used up to this many ranks
-constexpr int kMaxSweeps = 8;
+constexpr int kMaxSweeps = 40;      // worst case: one new spin bit per sweep (tiny test tiles)
 constexpr int kMaxPartialBlocks = 4096;   // upper bound on CTAs writing reduction partials
 constexpr int kMaxK = 2048;               // max Lanczos vectors
 constexpr int64_t kPartialDoubles = 4 << 20;   // 32 MB of per-CTA partial sums (>= kMaxPartialBlocks * 1024)

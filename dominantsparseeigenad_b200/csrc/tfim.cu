@@ -13,8 +13,10 @@
 //   sweep j : tile = 2^c contiguous x 2^h strided runs -> handles h spin bits starting at `hshift`
 //             (run stride 2^hshift doubles; c >= 2 keeps every global access a full 32 B sector,
 //             c >= 4 a full 128 B line)
-//   top log2(world) bits : whole-shard exchange with rank ^ (1<<j) over NCCL on a side stream,
-//             overlapped with the local sweeps and consumed by the last sweep.
+//   top log2(world) bits : the shard of rank ^ (1<<j) sits in slot j of this rank's peer arena, stored
+//             there over NVLink by the kernel that produced it (reorth pass 2, or push_kernel); the
+//             last sweep adds the slots.  Fallback: grouped ncclSend/ncclRecv on a side stream,
+//             overlapped with the local sweeps.
 // HBM bytes per element: 16 (first sweep: read v, write u) + 24 per extra sweep (read v, read u,
 // write u) + 8 per remote bit.  The dot-product epilogue (v.u for CG, or w.u) rides on the last sweep.
 #include "common.cuh"
@@ -286,6 +288,7 @@ static int plan_sweeps(int L, int Tmax, int run_bits, Sweep* out) {
                 if ((rem + (Tmax - cc) - 1) / (Tmax - cc) == nmin) c = cc;
         }
         if (c > T1) c = T1;
+        if (c > Tmax - 1) c = Tmax - 1;      // every strided sweep must handle at least one new bit
         if (c < 1) c = 1;
         int nsw = (rem + (Tmax - c) - 1) / (Tmax - c);
         while (rem > 0 && n < kMaxSweeps) {
@@ -440,4 +443,20 @@ extern "C" double dsea_tfim_diag(int N, int64_t s) {
     const uint64_t us = (uint64_t)s;
     const uint64_t rot = ((us << 1) | (us >> (N - 1))) & mask;
     return -(double)(N - 2 * __builtin_popcountll(us ^ rot));
+}
+
+// Host-callable view of the sweep schedule (for the CPU tests of the index logic): writes up to 40 rows
+// {T, c, hshift, b0} and returns the number of sweeps (negative on failure).
+extern "C" int dsea_tfim_plan(int local_bits, int tile_bits, int run_bits, int* out4x40) {
+    dsea::Sweep sw[dsea::kMaxSweeps];
+    if (tile_bits > 14) tile_bits = 14;
+    if (tile_bits < 3) tile_bits = 3;
+    const int n = dsea::plan_sweeps(local_bits, tile_bits, run_bits, sw);
+    for (int j = 0; j < n && j < dsea::kMaxSweeps; ++j) {
+        out4x40[4 * j + 0] = sw[j].T;
+        out4x40[4 * j + 1] = sw[j].c;
+        out4x40[4 * j + 2] = sw[j].hshift;
+        out4x40[4 * j + 3] = sw[j].b0;
+    }
+    return n;
 }
