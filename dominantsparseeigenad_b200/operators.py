@@ -179,6 +179,8 @@ class NativeOperator:
         work = empty(int(lib.dsea_cg_work_doubles(self.handle)), self.device)
         iters = C.c_int64(0)
         keep = self.param_ptr(param)
+        if maxit <= 0:
+            maxit = int(getattr(self, "dim", self.n_loc))      # CG.py:32 iterates at most n (GLOBAL dimension) times
         _lib.check(lib.dsea_cg(rt.handle, self.handle, keep[0], ptr(shift_), ptr(b_), ptr(x), ptr(work), eps, maxit,
                                C.byref(iters), stream_ptr()))
         runtime.stats["cg_calls"] += 1
