@@ -184,7 +184,7 @@ class NativeOperator:
         _lib.check(lib.dsea_cg(rt.handle, self.handle, keep[0], ptr(shift_), ptr(b_), ptr(x), ptr(work), eps, maxit,
                                C.byref(iters), stream_ptr()))
         runtime.stats["cg_calls"] += 1
-        runtime.stats["cg_iters"].append(int(iters.value))
+        runtime.record_cg_iterations(int(iters.value))
         return x
 
 
@@ -466,7 +466,7 @@ class CallbackOperator:
                 _lib.check(lib.dsea_cg_update(rt.handle, n, ptr(x), ptr(r), ptr(d), ptr(Ad), state if last else None, st))
             it += check_every
         runtime.stats["cg_calls"] += 1
-        runtime.stats["cg_iters"].append(int(state[1]))
+        runtime.record_cg_iterations(int(state[1]))
         return x
 
     def adjoint(self, v1, v2, param=None):

@@ -22,6 +22,14 @@ _draw_counter = 0
 stats = {"cg_iters": [], "lanczos_calls": 0, "cg_calls": 0}
 
 
+def record_cg_iterations(n: int, keep: int = 4096) -> None:
+    """Work accounting for bench.py / tests; bounded so long optimisation loops do not grow it forever."""
+    log = stats["cg_iters"]
+    log.append(int(n))
+    if len(log) > keep:
+        del log[:-keep]
+
+
 class Context:
     """Owns a dsea_ctx*.  rank/world follow torch.distributed when it is initialised."""
 
