@@ -48,6 +48,7 @@ struct SweepParams {
     int nrecv;
     int N, T, c, hshift, b0;
     int no_diag;            // 1: drop the diagonal (u = -g * flip sum), used for dH/dg
+    int use_tma;            // 1: stage contiguous tiles with cp.async.bulk + mbarrier (pipelined kernel only)
 };
 
 __device__ __forceinline__ double tfim_diag_dev(uint64_t s, int N, uint64_t mask) {
@@ -158,12 +159,51 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: used for CONTIGUOUS tiles, where one
+// elected thread moves the whole 64 KB tile with four instructions instead of 4096 LDGSTS.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
-    extern __shared__ __align__(16) double bufs[];               // 2 x 2^13 doubles
+    extern __shared__ __align__(128) double bufs[];              // 2 x 2^13 doubles
     __shared__ double red[32];
+    __shared__ __align__(8) uint64_t mbar[2];
     if (p.guard && *p.guard != 0.0) return;
     constexpr int T = kPipeT;
+    const bool tma = p.use_tma != 0;                             // contiguous tiles only (first sweep)
+    uint32_t phase[2] = {0u, 0u};
+    if (tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     const int c = p.c;
     const uint32_t cmask = (1u << c) - 1u;
     const int midbits = p.hshift - c;
@@ -185,8 +225,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
     auto gidx = [&](uint64_t base, uint32_t ee) -> uint64_t {
         return base | (ee & cmask) | ((uint64_t)(ee >> c) << p.hshift);
     };
-    auto prefetch = [&](uint64_t t, double* buf) {
+    auto prefetch = [&](uint64_t t, double* buf, int st) {
         const uint64_t base = tile_base(t);
+        if (tma) {
+            if (threadIdx.x == 0) {
+                constexpr uint32_t kChunk = (uint32_t)(sizeof(double) << T) / 4;           // 16 KB
+                mbar_expect_tx(&mbar[st], 4 * kChunk);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    tma_bulk_g2s(buf + q * (kChunk / 8), p.v + base + q * (kChunk / 8), kChunk, &mbar[st]);
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < kPipePairs; ++j) cp_async16(buf + e[j], p.v + gidx(base, e[j]));
         cp_async_commit();
@@ -194,19 +244,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
 
     uint64_t t = blockIdx.x;
     int stage = 0;
-    if (t < p.ntiles) prefetch(t, bufs);
+    if (t < p.ntiles) prefetch(t, bufs, 0);
     for (; t < p.ntiles; t += gridDim.x, stage ^= 1) {
         const double* buf = bufs + ((size_t)stage << T);
         const uint64_t tn = t + gridDim.x;
         const uint64_t base = tile_base(t);
-        if (tn < p.ntiles) prefetch(tn, bufs + ((size_t)(stage ^ 1) << T));
+        if (tn < p.ntiles) prefetch(tn, bufs + ((size_t)(stage ^ 1) << T), stage ^ 1);
         double2 ui[kPipePairs];
         if (MODE == MODE_ACCUM) {                                 // issue these HBM loads before waiting
 #pragma unroll
             for (int j = 0; j < kPipePairs; ++j) ui[j] = ldg2(p.uin + gidx(base, e[j]));
         }
-        if (tn < p.ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
-        __syncthreads();
+        if (tma) {
+            mbar_wait(&mbar[stage], phase[stage]);                // the bulk copy's bytes have landed
+            phase[stage] ^= 1u;
+        } else {
+            if (tn < p.ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();
+        }
 
         double2 x[kPipePairs], a[kPipePairs];
 #pragma unroll
@@ -376,6 +431,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.remote_scale = (p2p && prepushed) ? remote_scale : nullptr;
         p.guard = ctx->guard;
         p.no_diag = (!mode_adj && g == nullptr) ? 1 : 0;
+        p.use_tma = (ctx->tfim_tma && sw[j].c == sw[j].T && (((uintptr_t)v) & 127u) == 0) ? 1 : 0;
         p.nrecv = last ? nrecv : 0;
         p.rank_off = (uint64_t)ctx->rank << L;
         p.n_loc = (uint64_t)op->n_loc;

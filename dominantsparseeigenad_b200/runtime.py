@@ -93,7 +93,7 @@ def context() -> Context:
         for key, env in (("tfim_tile_bits", "DSEA_TFIM_TILE_BITS"), ("tfim_run_bits", "DSEA_TFIM_RUN_BITS"),
                          ("cg_check_every", "DSEA_CG_CHECK_EVERY"), ("reorth_ctas_per_sm", "DSEA_REORTH_CTAS"),
                          ("p2p", "DSEA_P2P"), ("tfim_pipeline", "DSEA_TFIM_PIPELINE"),
-                         ("mailbox", "DSEA_MAILBOX")):
+                         ("mailbox", "DSEA_MAILBOX"), ("tfim_tma", "DSEA_TFIM_TMA")):
             if os.environ.get(env):
                 _ctx.set_option(key, int(os.environ[env]))
     return _ctx

@@ -53,8 +53,9 @@ def main():
         dot = torch.empty(1, dtype=torch.float64, device="cuda")
         res = {}
         ref = None
-        for pipe in (0, 1):
+        for pipe, tma in ((0, 0), (1, 0), (1, 1)):
             rt.set_option("tfim_pipeline", pipe)
+            rt.set_option("tfim_tma", tma)
             st = stream_ptr()
             plain = lambda: _lib.check(lib.dsea_matvec(rt.handle, m.handle, ptr(g), None, ptr(v), ptr(u), None, None, st))
             cgmv = lambda: _lib.check(lib.dsea_matvec(rt.handle, m.handle, ptr(g), ptr(sh), ptr(v), ptr(u), dot.data_ptr(), None, st))
@@ -69,11 +70,12 @@ def main():
                 err = (u - ref).abs().max().item() / ref.abs().max().item()
             adj()
             adjval = dot.item()
-            res[f"pipeline{pipe}"] = {"matvec_ms": t_plain, "matvec_GBps_of_16n": 16 * n / t_plain / 1e6,
+            res[f"pipeline{pipe}_tma{tma}"] = {"matvec_ms": t_plain, "matvec_GBps_of_16n": 16 * n / t_plain / 1e6,
                                       "matvec_cg_ms": t_cg, "adjoint_ms": t_adj,
                                       "adjoint_GBps_of_16n": 16 * n / t_adj / 1e6, "rel_diff_vs_generic": err,
                                       "adjoint_value": adjval}
         rt.set_option("tfim_pipeline", 1)
+        rt.set_option("tfim_tma", 0)
         res["bounds_ms_at_6540GBps"] = {"algorithmic_16n": 16 * n / 6540e6, "two_sweep_hbm_40n": 40 * n / 6540e6}
         out.append({"spins": N, **res})
         del m, v, w, u, ref
