@@ -131,7 +131,7 @@ struct dsea_ctx {
     int tfim_tile_bits = 13;
     int tfim_run_bits = 0;              // 0 = auto
     int tfim_pipeline = 1;              // persistent double-buffered sweep kernel for full 2^13 tiles
-    int tfim_tma = 0;                   // stage contiguous tiles with TMA bulk copies instead of LDGSTS
+    int tfim_tma = 1;                   // stage contiguous tiles with TMA bulk copies (UBLKCP + mbarrier) instead of LDGSTS
     int cg_check_every = 16;
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
 };
