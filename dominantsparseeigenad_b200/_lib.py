@@ -73,6 +73,7 @@ PROTOTYPES = {
 }
 
 DSEA_MIN, DSEA_MAX, DSEA_BOTH = 0, 1, 2
+DSEA_ERR_NOCONV = -4
 
 _lib = None
 
@@ -99,7 +100,18 @@ def load() -> C.CDLL:
     return lib
 
 
-def check(status: int) -> None:
-    if status != 0:
-        msg = load().dsea_last_error()
-        raise DseaError(f"libdsea error {status}: {msg.decode() if msg else '?'}")
+class ConvergenceWarning(RuntimeWarning):
+    """CG reached its iteration cap (or a NaN residual) before |r| < eps.  The reference returns the last
+    iterate silently in that case (CG.py:32); here the iterate is returned as well, with this warning."""
+
+
+def check(status: int, allow_noconv: bool = False) -> None:
+    if status == 0:
+        return
+    msg = load().dsea_last_error()
+    text = msg.decode() if msg else "?"
+    if status == DSEA_ERR_NOCONV and allow_noconv:
+        import warnings
+        warnings.warn(text, ConvergenceWarning, stacklevel=3)
+        return
+    raise DseaError(f"libdsea error {status}: {text}")

@@ -23,10 +23,12 @@ struct ProfRec {
     cudaEvent_t a, b;
     int kind;
     double bytes;
+    int64_t guard_key;             // >= 0: launched under the CG done flag as step `guard_key` of the running solve
 };
 struct Profiler {
     std::vector<ProfRec> recs;     // event pool, reused across collections
     size_t used = 0;
+    int64_t guard_key = -1;        // set by dsea_cg around the launches it guards (2*iteration + phase)
 };
 
 int prof_begin(dsea_ctx* ctx, int kind, double bytes, cudaStream_t st) {
@@ -40,6 +42,7 @@ int prof_begin(dsea_ctx* ctx, int kind, double bytes, cudaStream_t st) {
     ProfRec& r = p->recs[p->used];
     r.kind = kind;
     r.bytes = bytes;
+    r.guard_key = p->guard_key;
     cudaEventRecord(r.a, st);
     return (int)p->used++;
 }
@@ -48,6 +51,32 @@ void prof_end(dsea_ctx* ctx, int token, cudaStream_t st) {
     if (token < 0 || !ctx->prof) return;
     cudaEventRecord(ctx->prof->recs[token].b, st);
 }
+
+void prof_guard_key(dsea_ctx* ctx, int64_t key) {
+    if (ctx->prof) ctx->prof->guard_key = key;
+}
+
+// Launches guarded by the CG done flag exit immediately once it is set.  After the solve the executed
+// iteration count is known, so every record issued for a later step is re-labelled PK_NOOP: it keeps its
+// (tiny) elapsed time but is credited no bytes and does not count as a launch of its kernel.
+void prof_retire_guarded(dsea_ctx* ctx, size_t first, int64_t first_noop_key) {
+    Profiler* p = ctx->prof;
+    if (!p) return;
+    for (size_t i = first; i < p->used; ++i) {
+        ProfRec& r = p->recs[i];
+        if (r.guard_key >= 0 && r.guard_key >= first_noop_key) {
+            r.kind = PK_NOOP;
+            r.bytes = 0.0;
+        }
+        r.guard_key = -1;
+    }
+}
+
+void prof_guard_next_phase(dsea_ctx* ctx) {
+    if (ctx->prof && ctx->prof->guard_key >= 0) ctx->prof->guard_key += 1;
+}
+
+size_t prof_mark(const dsea_ctx* ctx) { return ctx->prof ? ctx->prof->used : 0; }
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
@@ -274,7 +303,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     if (!strcmp(key, "tfim_tile_bits")) ctx->tfim_tile_bits = (int)value;
     else if (!strcmp(key, "tfim_run_bits")) ctx->tfim_run_bits = (int)value;
     else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
-    else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (int)value;
+    else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);
@@ -494,6 +523,7 @@ int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double*
     DSEA_TRY(apply_op(ctx, op, param, shift, x, Ad, nullptr, opwork, st));             // CG.py:27
     DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st));
     ctx->guard = ctx->scal + S_DONE;
+    const size_t prof_first = prof_mark(ctx);
     int status = DSEA_OK;
     int64_t issued = 0;
     int slot = 0;
@@ -502,6 +532,7 @@ int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double*
     while (!finished) {
         const int64_t chunk = ctx->cg_check_every;
         for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
+            prof_guard_key(ctx, 2 * (issued + q));
             status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st);   // one matvec / iteration
             if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st);
         }
@@ -519,12 +550,20 @@ int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double*
         if (issued >= maxit) finished = true;
     }
     ctx->guard = nullptr;
+    prof_guard_key(ctx, -1);
     if (status != DSEA_OK) return status;
     DSEA_TRY(cg_poll(ctx, slot, st));
     DSEA_CUDA(cudaStreamSynchronize(st));
-    const double done = ctx->pinned[8 * slot], iters = ctx->pinned[8 * slot + 1];
+    const double done = ctx->pinned[8 * slot], iters = ctx->pinned[8 * slot + 1], rnorm = ctx->pinned[8 * slot + 2];
     if (iters_host) *iters_host = (int64_t)iters;
-    (void)done;
+    // iteration `iters - 1` set the flag in its scalar kernel: its direction update (key 2*(iters-1)+1) and
+    // everything issued afterwards were no-ops
+    prof_retire_guarded(ctx, prof_first, done != 0.0 ? 2 * (int64_t)iters - 1 : INT64_MAX);
+    if (done != 1.0) {        // 2: iteration cap or NaN residual; 0: loop left without the flag (cannot happen)
+        set_error("CG stopped after %lld iterations with |r| = %.3e >= eps = %.3e (CG.py:32 returns silently here)",
+                  (long long)iters, rnorm, eps);
+        return DSEA_ERR_NOCONV;
+    }
     return DSEA_OK;
 }
 

@@ -102,8 +102,12 @@ __global__ void cg_scalar_kernel(double* scal) {
     scal[S_ITERS] = it;
     const double rn = sqrt(rr_new);
     scal[S_RNORM] = rn;
-    if (rn < scal[S_EPS] || it >= scal[S_MAXIT] || !(rn == rn)) {
+    if (rn < scal[S_EPS]) {                  // converged (CG.py:35)
         scal[S_DONE] = 1.0;
+        return;
+    }
+    if (it >= scal[S_MAXIT] || !(rn == rn)) {   // iteration cap (CG.py:32) or NaN: reported as DSEA_ERR_NOCONV
+        scal[S_DONE] = 2.0;
         return;
     }
     scal[S_BETA] = rr_new / scal[S_RR];
@@ -156,6 +160,7 @@ int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const 
     DSEA_CUDA(cudaGetLastError());
     DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
     cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    prof_guard_next_phase(ctx);
     tok = prof_begin(ctx, PK_CG_UPDATE, 24.0 * (double)n, st);
     cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal);
     prof_end(ctx, tok, st);

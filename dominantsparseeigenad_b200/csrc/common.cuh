@@ -87,7 +87,7 @@ struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
 struct Profiler;  // optional per-kernel CUDA-event timing (api.cu)
 
 enum ProfKind { PK_MATVEC = 0, PK_REORTH_DOTS, PK_REORTH_UPDATE, PK_RITZ, PK_CG_UPDATE, PK_NORMALISE, PK_TRIDIAG,
-                PK_ADJOINT, PK_COUNT };
+                PK_ADJOINT, PK_NOOP, PK_EXCHANGE, PK_COUNT };
 
 }  // namespace dsea
 
@@ -217,6 +217,8 @@ inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
 // Per-kernel timing with CUDA events on the launching stream (no-ops unless dsea_profile_enable()).
 int prof_begin(dsea_ctx* ctx, int kind, double algorithmic_bytes, cudaStream_t st);
 void prof_end(dsea_ctx* ctx, int token, cudaStream_t st);
+void prof_guard_key(dsea_ctx* ctx, int64_t key);      // tags the following records as guarded step `key` (-1: none)
+void prof_guard_next_phase(dsea_ctx* ctx);            // key += 1 (direction update of the same CG iteration)
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -230,16 +230,19 @@ reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __
     }
 }
 
-static inline int reorth_grid(const dsea_ctx* ctx, int64_t n) {
+// `m` = partial sums each CTA writes (pass 1: one per column): grid * m must fit ctx->partials.
+static inline int reorth_grid(const dsea_ctx* ctx, int64_t n, int m = 1) {
     const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
     int64_t cap = (int64_t)ctx->num_sms * ctx->reorth_ctas_per_sm;
     if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
+    if (cap * m > kPartialDoubles) cap = kPartialDoubles / m;
+    if (cap < 1) cap = 1;
     return (int)(ntiles < cap ? ntiles : cap);
 }
 
 int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, double* c_out,
                 cudaStream_t st, const Recurrence* rec) {
-    const int grid = reorth_grid(ctx, n);
+    const int grid = reorth_grid(ctx, n, m);
     const size_t smem = (size_t)8 * m * sizeof(double);
     DSEA_ARG(smem <= 200 * 1024, "too many Lanczos vectors for the reorth accumulators");
     static size_t smem_set = 0;

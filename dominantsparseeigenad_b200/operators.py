@@ -96,13 +96,16 @@ class Project(torch.autograd.Function):
         out = empty(b_.numel(), rt.device)
         _lib.check(rt.lib.dsea_project(rt.handle, b_.numel(), ptr(psi_), ptr(b_), ptr(out), stream_ptr()))
         ctx.save_for_backward(psi, b)
-        return out
+        return out.to(b.device)             # CPU tensors in => CPU tensors out, like Scale and Dot's callers
 
     @staticmethod
     def backward(ctx, go):
         psi, b = ctx.saved_tensors
-        grad_b = Project.apply(psi, go)
-        grad_psi = -scale(dot(psi, b), go) - scale(dot(go, psi), b)
+        grad_b = Project.apply(psi, go).to(b.device) if ctx.needs_input_grad[1] else None
+        grad_psi = None
+        if ctx.needs_input_grad[0]:
+            go_p, b_p = go.to(psi.device), b.to(psi.device)
+            grad_psi = -scale(dot(psi, b_p).to(psi.device), go_p) - scale(dot(go_p, psi).to(psi.device), b_p)
         return grad_psi, grad_b
 
 
@@ -182,7 +185,7 @@ class NativeOperator:
         if maxit <= 0:
             maxit = int(getattr(self, "dim", self.n_loc))      # CG.py:32 iterates at most n (GLOBAL dimension) times
         _lib.check(lib.dsea_cg(rt.handle, self.handle, keep[0], ptr(shift_), ptr(b_), ptr(x), ptr(work), eps, maxit,
-                               C.byref(iters), stream_ptr()))
+                               C.byref(iters), stream_ptr()), allow_noconv=True)
         runtime.stats["cg_calls"] += 1
         runtime.record_cg_iterations(int(iters.value))
         return x
@@ -467,6 +470,10 @@ class CallbackOperator:
             it += check_every
         runtime.stats["cg_calls"] += 1
         runtime.record_cg_iterations(int(state[1]))
+        if state[2] != 1.0:
+            import warnings
+            warnings.warn(f"CG stopped after {int(state[1])} iterations with |r| = {state[0]:.3e} >= eps = {eps:.3e} "
+                          "(CG.py:32 returns silently here)", _lib.ConvergenceWarning, stacklevel=2)
         return x
 
     def adjoint(self, v1, v2, param=None):

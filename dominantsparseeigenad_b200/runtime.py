@@ -19,6 +19,7 @@ F64 = torch.float64
 _ctx = None
 _start_vector_hook: Optional[Callable[[int, str], Optional[torch.Tensor]]] = None
 _draw_counter = 0
+_draw_seed = None
 stats = {"cg_iters": [], "lanczos_calls": 0, "cg_calls": 0}
 
 
@@ -70,7 +71,7 @@ class Context:
         return int(self.lib.dsea_launch_count(self.handle))
 
     PROFILE_KINDS = ("matvec", "reorth_dots", "reorth_update", "ritz", "cg_update", "normalise", "tridiag",
-                     "adjoint")
+                     "adjoint", "noop", "exchange")
 
     def profile_enable(self, on: bool = True) -> None:
         _lib.check(self.lib.dsea_profile_enable(self.handle, 1 if on else 0))
@@ -135,13 +136,22 @@ def set_start_vector_hook(fn: Optional[Callable[[int, str], Optional[torch.Tenso
     _start_vector_hook = fn
 
 
+def reset_draw_counter() -> None:
+    """Restarts the start-vector stream (the next draw is draw 1 of the current torch seed)."""
+    global _draw_counter
+    _draw_counter = 0
+
+
 def start_vector(n_loc: int, kind: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Standard-normal start vector on the GPU.  Reference: torch.randn at Lanczos.py:52, CG.py:58,121.
 
-    Reproducible under torch.manual_seed: the Philox key is torch's initial seed and the stream id a
-    per-process draw counter.  The counter is global-index based, so sharded runs draw the same vector.
+    Reproducible under torch.manual_seed: the Philox key is torch's initial seed and the stream id a draw
+    counter that restarts whenever that seed changes (so `manual_seed(s)` followed by the same sequence of
+    solves draws the same vectors; re-seeding with the SAME value does not restart it — call
+    `reset_draw_counter()` for that).  The Philox counter is the global element index, so sharded runs draw
+    the same vector as a single GPU.
     """
-    global _draw_counter
+    global _draw_counter, _draw_seed
     ctx = context()
     if out is None:
         out = empty(n_loc, ctx.device)
@@ -150,7 +160,9 @@ def start_vector(n_loc: int, kind: str, out: Optional[torch.Tensor] = None) -> t
         if v is not None:
             out.copy_(v.to(device=ctx.device, dtype=F64))
             return out
-    _draw_counter += 1
     seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if seed != _draw_seed:
+        _draw_seed, _draw_counter = seed, 0
+    _draw_counter += 1
     _lib.check(ctx.lib.dsea_randn(ctx.handle, n_loc, seed, _draw_counter, ptr(out), stream_ptr()))
     return out
