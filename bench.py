@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """bench.py — forward+backward seconds per dominant-eigenpair solve on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload E0_dE0|chiF]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one solve of the TFIM ground state through the reference-shaped public API:
     E0, psi0 = DominantSparseSymeig.apply(g, k, dim)         Lanczos, k vectors, full reorthogonalisation
     dE0,     = torch.autograd.grad(E0, g)                    CG solve of (H - E0) x = b + adjoint contraction
-(examples/TFIM/E0.py:60-63 shape).  At 1 GPU the workload is TFIM N=24, k=200 — the largest BASELINE
-configuration whose fp64 Lanczos basis (26.8 GB) fits one GPU; at P GPUs the state vector is sharded by
-its top log2(P) spin bits with n_loc = 2^24 amplitudes per GPU (weak scaling: N = 24 + log2 P).
+(examples/TFIM/E0.py:60-63 shape; `--workload chiF` runs examples/TFIM/chiF.py:46-53 instead: one forward and
+two nested backward passes = three CG solves).  At 1 GPU the workload is TFIM N=24, k=200 — the largest
+BASELINE configuration whose fp64 Lanczos basis (26.8 GB) fits one GPU; at P GPUs the state vector is sharded
+by its top log2(P) spin bits with n_loc = 2^24 amplitudes per GPU (weak scaling: N = 24 + log2 P).
 
-Prints ONE JSON line (rank 0).  `value` = device-timed seconds per solve with g resident in HBM;
-`e2e` = the same through host buffers (g from pinned host memory, E0 / dE0 / psi0 copied back);
-`roofline` = the dominant kernel (re-orthogonalisation pass 2) timed live with CUDA events inside the
-timed region; `cpu_baseline` = the CPU oracle (restatement of the reference's PyTorch-CPU path) on a
-bounded sample.  `--impl reference` times only that CPU path.
+Prints ONE JSON line (rank 0).
+  value         device-timed seconds per solve with g resident in HBM;
+  e2e           the same through host buffers (g from pinned host memory, E0 / dE0 / psi0 copied back);
+  roofline      the dominant kernel (re-orthogonalisation pass 2) timed live with CUDA events in the timed region;
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref) timed on the host cores on a bounded sample — TFIM N=20,
+                k=100 (BASELINE config 2) — `value` is the MEASURED time of that sample, never an extrapolation;
+  pairs         the same sample solved by this library in the same run, so a measured same-config ratio exists;
+  headline      (P >= 4) TFIM N=28, k=200 (BASELINE config 4) and (P = 8) N=30, k=200 (config 5, fp32 shadow basis)
+                measured in the same process after the weak-scaling line;
+  selfcheck     (P > 1) parity of the sharded path against exact identities and closed forms.
+`--impl reference` times only the reference's CPU path: the product configuration itself when the host can run
+it inside the time budget (N <= 24), otherwise the bounded sample, labelled as what it is.
 """
 from __future__ import annotations
 
@@ -37,6 +45,7 @@ import torch  # noqa: E402
 METRIC = "tfim_fwd_bwd_seconds_per_solve"
 UNIT = "s/solve"
 SAMPLE_N, SAMPLE_K = 20, 100          # CPU sample: BASELINE config 2 shape (largest upstream fixture size)
+MODES = {"E0_dE0": "E0_plus_dE0dg", "chiF": "chiF"}
 
 
 def parse():
@@ -45,11 +54,18 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="E0_dE0", choices=sorted(MODES))
     ap.add_argument("--spins", type=int, default=0, help="override N (default 24 + log2 gpus)")
-    ap.add_argument("--k", type=int, default=200, help="Lanczos vectors; 0 = largest k <= 200 whose fp64 basis fits HBM")
+    ap.add_argument("--k", type=int, default=200, help="Lanczos vectors; 0 = largest k <= 200 whose basis fits HBM")
     ap.add_argument("--g", type=float, default=1.0)
+    ap.add_argument("--basis", default="fp64", choices=["fp64", "fp32"],
+                    help="storage of the Lanczos basis (fp32 = opt-in shadow basis with fp64 accumulation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-spins", type=int, default=SAMPLE_N)
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-2 pair / headline configs / selfcheck")
+    ap.add_argument("--cpu-sample-spins", type=int, default=SAMPLE_N, help="(tests) shrink the bounded CPU sample")
+    ap.add_argument("--cpu-sample-k", type=int, default=SAMPLE_K)
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("DSEA_REF_BUDGET_S", 420)),
+                    help="reference arm: wall-clock budget for attempting the product configuration itself")
     return ap.parse_args()
 
 
@@ -114,124 +130,180 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (port of the reference's PyTorch-CPU path) on a bounded sample
+# CPU side: the unmodified reference (baseline/_ref) or, if it is not staged, the oracle port
 # ------------------------------------------------------------------------------------------------
-class _TimedCalls:
-    def __init__(self, fn):
-        self.fn, self.calls, self.seconds = fn, 0, 0.0
-
-    def __call__(self, v):
-        t = time.perf_counter()
-        out = self.fn(v)
-        self.seconds += time.perf_counter() - t
-        self.calls += 1
-        return out
+def workload_name(N, k, mode):
+    return f"tfim_N{N}_k{k}_{MODES[mode]}"
 
 
-def cpu_sample_solve(model, k, seed):
-    """One E0 + dE0/dg solve with the oracle; returns timings split into operator / other work."""
+def host_info():
+    info = {"cores": os.cpu_count() or 1}
+    try:
+        import psutil
+        vm = psutil.virtual_memory()
+        info["ram_total_gb"], info["ram_available_gb"] = vm.total / 1e9, vm.available / 1e9
+    except Exception:
+        pass
+    return info
+
+
+def _port_solve(N, k, g, mode, seed):
+    """Fallback when baseline/_ref is absent: the oracle's restatement of the same path (kind = "port")."""
     from oracle import dsea_oracle as orc
-    H = _TimedCalls(model.H)
+    model = orc.TFIMOracle(N, torch.tensor([g], dtype=torch.float64, requires_grad=True))
     stats = {}
-    model.g = model.g.detach().clone().requires_grad_(True)
-    Dom, _ = orc.make_sparse_primitives(H, model.Hadjoint_to_gadjoint, orc.SeededDraws(seed), stats)
+    Dom, _ = orc.make_sparse_primitives(model.H, model.Hadjoint_to_gadjoint, orc.SeededDraws(seed), stats)
     t0 = time.perf_counter()
     E0, psi0 = Dom.apply(model.g, k, model.dim)
     t1 = time.perf_counter()
-    mv_fwd, calls_fwd = H.seconds, H.calls
-    dE0, = torch.autograd.grad(E0, model.g)
+    if mode == "chiF":
+        logF = torch.log(psi0.detach().matmul(psi0))
+        d1, = torch.autograd.grad(logF, model.g, create_graph=True)
+        d2, = torch.autograd.grad(d1, model.g)
+        extra = {"chiF": -d2.item()}
+    else:
+        dE0, = torch.autograd.grad(E0, model.g)
+        extra = {"dE0": dE0.item()}
     t2 = time.perf_counter()
-    return {"fwd": t1 - t0, "bwd": t2 - t1, "mv_fwd": mv_fwd, "calls_fwd": calls_fwd,
-            "mv_bwd": H.seconds - mv_fwd, "calls_bwd": H.calls - calls_fwd, "cg_iters": stats["cg_iters"][-1],
-            "E0": E0.item(), "dE0": dE0.item()}
+    return {"N": N, "k": k, "g": g, "mode": mode, "fwd": t1 - t0, "bwd": t2 - t1, "total": t2 - t0, "E0": E0.item(),
+            **extra}
 
 
-def scale_cpu_sample(t, Ns, ks, Nw, kw):
-    """Extrapolates a sample solve (Ns spins, ks vectors) to the bench workload (Nw, kw) with the
-    reference's own cost model: the operator application moves (16N+24) 2^N bytes per
-    call; the re-orthogonalisation on the row-major (n, k) basis and the k x k Ritz GEMM scale as
-    2^N k^2; CG work scales with the operator (iteration count held at the sample's — an underestimate)."""
+def cpu_solve(N, k, g, mode, seed=1234):
+    """(kind, timing dict) of ONE measured CPU solve at exactly (N, k, g, mode)."""
+    from baseline import ref_runner
+    if ref_runner.available():
+        ref_runner.warm(N)
+        return "reference", ref_runner.solve(N, k, g, mode, seed)
+    return "port", _port_solve(N, k, g, mode, seed)
+
+
+def predict_seconds(t, Ns, ks, Nw, kw):
+    """Planning estimate ONLY (never reported as a measurement): scales a measured sample solve to another size
+    with the reference's own cost model: operator ~ (16N+24) 2^N bytes per call, reorth and the
+    Ritz GEMM ~ 2^N k^2, CG iteration count held fixed.  Used to decide whether a full-size run fits the budget."""
     rn = 2.0 ** (Nw - Ns)
     op = rn * (16 * Nw + 24) / (16 * Ns + 24)
-    fwd = t["mv_fwd"] * op * (kw / ks) + (t["fwd"] - t["mv_fwd"]) * rn * (kw / ks) ** 2
-    bwd = t["bwd"] * op
-    return fwd + bwd
+    fwd = t.get("mv_fwd", 0.5 * t["fwd"])
+    return fwd * op * (kw / ks) + (t["fwd"] - fwd) * rn * (kw / ks) ** 2 + t["bwd"] * op
 
 
-def run_cpu_arm(args, steps, warmup, Nw, kw):
-    from oracle import dsea_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    Ns, ks = args.cpu_sample_spins, SAMPLE_K
-    model = orc.TFIMOracle(Ns, torch.tensor([args.g], dtype=torch.float64))
-    model.H(torch.randn(model.dim, dtype=torch.float64))        # first application is 4-5x slower (page faults)
-    times, last = [], None
-    for i in range(warmup + steps):
-        if i < warmup and i >= 1:
-            continue                                             # one warm-up solve is enough on the CPU
-        last = cpu_sample_solve(model, ks, 100 + i)
-        if i >= warmup:
-            times.append(last)
-    med = lambda key: statistics.median(t[key] for t in times)
-    tmed = {key: med(key) for key in ("fwd", "bwd", "mv_fwd", "mv_bwd")}
-    measured = tmed["fwd"] + tmed["bwd"]
-    scaled = scale_cpu_sample(tmed, Ns, ks, Nw, kw)
-    sample = (f"oracle port of the reference PyTorch-CPU path: TFIM N={Ns}, k={ks}, g={args.g}, E0+dE0/dg, "
-              f"{len(times)} solve(s), measured {measured:.2f} s/solve (fwd {tmed['fwd']:.2f} s with "
-              f"{last['calls_fwd']} operator calls, bwd {tmed['bwd']:.2f} s with {last['calls_bwd']} calls, "
-              f"{last['cg_iters']} CG iterations); value = that scaled to N={Nw}, k={kw} by the reference's own "
-              f"byte model (operator ~ (16N+24)2^N per call, reorth/Ritz ~ 2^N k^2, CG iterations held fixed)")
-    return {"value": scaled, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "measured_sample_seconds": measured}
+def cpu_baseline_leg(args, mode):
+    """Bounded sample for the product arm's `cpu_baseline`: one measured solve at N=20, k=100."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    kind, t = cpu_solve(SAMPLE_N, SAMPLE_K, args.g, mode)
+    return {"value": t["total"], "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample_workload": workload_name(SAMPLE_N, SAMPLE_K, mode),
+            "sample": (f"ONE measured solve of TFIM N={SAMPLE_N}, k={SAMPLE_K}, g={args.g} ({MODES[mode]}) by the "
+                       f"{'unmodified reference staged under baseline/_ref' if kind == 'reference' else 'oracle port'}"
+                       f" on {torch.get_num_threads()} host threads after one warm-up operator application: "
+                       f"fwd {t['fwd']:.2f} s + bwd {t['bwd']:.2f} s; value is that measurement, NOT scaled to the "
+                       f"bench workload"),
+            "detail": t}
 
 
-def exact_tfim_energy(N, g):
-    """Exact finite-N ground-state energy of the periodic TFIM chain and dE0/dg (free fermions,
-    Neveu-Schwarz momenta k = (2m+1) pi / N; cf. examples/TFIM/E0.py:15-20 of the reference)."""
-    import math
-    ks = [(2 * m + 1) * math.pi / N for m in range(N)]
-    eps = [2.0 * math.sqrt(g * g - 2.0 * g * math.cos(k) + 1.0) for k in ks]
-    dE = -0.5 * sum(4.0 * (g - math.cos(k)) / e for k, e in zip(ks, eps) if e > 0.0)
-    return -0.5 * sum(eps), dE
+def run_reference_arm(args, N, k, mode, config):
+    """`--impl reference`: measures the reference's own CPU path.  Returns the JSON line."""
+    t_start = time.perf_counter()
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    host = host_info()
+    from baseline import ref_runner
+    kind, sample = cpu_solve(SAMPLE_N, SAMPLE_K, args.g, mode)
+    attempt = {"attempted": False}
+    full = None
+    need_gb = ref_runner.required_host_bytes(N, k) / 1e9
+    if (N, k) == (SAMPLE_N, SAMPLE_K):
+        full = sample
+    elif N > 25:
+        attempt["why_not"] = (f"the reference cannot run N={N}: its (2^N, N) int64 flip table alone is "
+                              f"{8 * N * 2 ** N / 1e9:.0f} GB (TFIM.py:48-51)")
+    elif host.get("ram_available_gb", 0.0) < 1.15 * need_gb:
+        attempt["why_not"] = f"needs ~{need_gb:.0f} GB of host RAM, {host.get('ram_available_gb', 0):.0f} GB available"
+    else:
+        pred = predict_seconds(sample, SAMPLE_N, SAMPLE_K, N, k)
+        attempt["predicted_seconds"] = pred
+        left = args.ref_budget_s - (time.perf_counter() - t_start)
+        if pred > 0.8 * left:
+            attempt["why_not"] = f"predicted {pred:.0f} s exceeds the {args.ref_budget_s:.0f} s budget (--ref-budget-s)"
+        elif not ref_runner.available():
+            attempt["why_not"] = "baseline/_ref is not staged"
+        else:
+            attempt["attempted"] = True
+            cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_runner.py"), "--spins", str(N), "--k", str(k),
+                   "--g", str(args.g), "--mode", mode]
+            try:       # own process: ~60 GB of host memory is returned to the OS afterwards, and it can be timed out
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=left)
+                if out.returncode == 0:
+                    full = json.loads(out.stdout.strip().splitlines()[-1])
+                else:
+                    attempt["why_not"] = "full-size run failed: " + out.stderr.strip()[-300:]
+            except subprocess.TimeoutExpired:
+                attempt["why_not"] = f"full-size run exceeded the remaining budget ({left:.0f} s) and was stopped"
+    if full is not None:
+        measured, Nm, km = full, N, k
+        config = dict(config)
+    else:
+        measured, Nm, km = sample, SAMPLE_N, SAMPLE_K
+        config = dict(config, workload=workload_name(Nm, km, mode), spins=Nm, lanczos_vectors=km,
+                      sharding="host_cpu", product_workload=workload_name(N, k, mode),
+                      note="bounded sample: the product workload itself was not run on the CPU (see cpu_baseline.attempt)")
+        config.pop("l2", None)
+    value = measured["total"]
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": (f"ONE measured solve of {workload_name(Nm, km, mode)} at g={args.g} by the "
+                      f"{'unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port'} on {cores} "
+                      f"host threads: fwd {measured['fwd']:.2f} s, bwd {measured['bwd']:.2f} s"),
+           "sample_workload": workload_name(Nm, km, mode), "detail": measured, "attempt": attempt, "host": host}
+    if full is not None and (Nm, km) != (SAMPLE_N, SAMPLE_K):
+        cpu["config2_sample"] = {"workload": workload_name(SAMPLE_N, SAMPLE_K, mode), "value": sample["total"],
+                                 "detail": sample}
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_seconds": time.perf_counter() - t_start}
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main():
+    global SAMPLE_N, SAMPLE_K
     args = parse()
+    SAMPLE_N, SAMPLE_K = args.cpu_sample_spins, args.cpu_sample_k
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     log2w = max(world, 1).bit_length() - 1
+    mode = args.workload
     N = args.spins or (24 + log2w)
     k = args.k
+    bytes_per = 4 if args.basis == "fp32" else 8
     if args.impl == "ours" and k <= 0:
-        # capacity policy (SURVEY 7.3-1): the fp64 basis is k * 8 * n_loc bytes per GPU; keep 16 vectors + 2 GB
+        # capacity policy (SURVEY 7.3-1): the basis is k * bytes_per * n_loc bytes per GPU; keep 16 fp64 vectors + 2 GB
         # for the matvec / CG work space, the peer arena and the eigenvector.
         torch.cuda.set_device(local_rank)
         free_b, _ = torch.cuda.mem_get_info()
         vec_b = 8 * 2 ** (N - log2w)
-        k = int(max(2, min(200, (free_b - 16 * vec_b - 2e9) // vec_b)))
+        k = int(max(2, min(200, (free_b - 16 * vec_b - 2e9) // (vec_b * bytes_per // 8))))
     elif k <= 0:
         k = 200
-    config = {"workload": f"tfim_N{N}_k{k}_E0_plus_dE0dg", "spins": N, "lanczos_vectors": k, "g": args.g,
-              "sharding": f"top{log2w}bits_x{world}" if world > 1 else "single_gpu",
-              "l2": "inputs_exceed_l2 (Lanczos basis %.1f GB per GPU)" % (k * 2.0 ** (N - log2w) * 8 / 1e9),
-              "cg": "as reference: eps=1e-7 absolute, random projected x0 (CG.py:25,121-122)"}
+
+    def make_config(N_, k_, basis):
+        return {"workload": workload_name(N_, k_, mode), "spins": N_, "lanczos_vectors": k_, "g": args.g,
+                "sharding": f"top{log2w}bits_x{world}" if world > 1 else "single_gpu", "basis": basis,
+                "l2": "inputs_exceed_l2 (Lanczos basis %.1f GB per GPU)"
+                      % (k_ * 2.0 ** (N_ - log2w) * (4 if basis == "fp32" else 8) / 1e9),
+                "cg": "as reference: eps=1e-7 absolute, random projected x0 (CG.py:25,121-122)"}
+
+    config = make_config(N, k, args.basis)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        t0 = time.perf_counter()
-        cpu = run_cpu_arm(args, max(1, min(args.steps, 3)), min(args.warmup, 1), N, k)
-        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["measured_sample_seconds"] * 1e3,
-                "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": config, "cpu_baseline": cpu,
-                "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0, "wall_seconds": time.perf_counter() - t0}
-        print(json.dumps(line))
+        print(json.dumps(run_reference_arm(args, N, k, mode, config)))
         return
 
     import torch.distributed as dist
@@ -239,33 +311,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import dominantsparseeigenad_b200 as dsea
+    from dominantsparseeigenad_b200.analytic import tfim_exact
     rt = dsea.runtime.context()
     dev = rt.device
-    model = dsea.TFIM(N)
-    dsea.symeig.setDominantSparseSymeig(model.H, model.Hadjoint_to_gadjoint)
-    solve = dsea.symeig.DominantSparseSymeig.apply
-    n_loc = model.n_loc
-
-    g_host = torch.tensor([args.g], dtype=torch.float64).pin_memory()
-    out_host = torch.empty(2, dtype=torch.float64).pin_memory()
-    psi_host = torch.empty(n_loc, dtype=torch.float64).pin_memory()
-    g_dev = g_host.to(dev)
-    results = {}
-
-    def step_device():
-        model.g = g_dev.detach().requires_grad_(True)
-        E0, psi0 = solve(model.g, k, model.dim, dev)
-        dE0, = torch.autograd.grad(E0, model.g)
-        results["E0"], results["dE0"] = E0, dE0
-
-    def step_e2e():
-        model.g = g_host.to(dev, non_blocking=True).requires_grad_(True)
-        E0, psi0 = solve(model.g, k, model.dim, dev)
-        dE0, = torch.autograd.grad(E0, model.g)
-        out_host[0:1].copy_(E0.detach().reshape(1), non_blocking=True)
-        out_host[1:2].copy_(dE0.detach().reshape(1), non_blocking=True)
-        psi_host.copy_(psi0.detach(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
     def barrier():
         if world > 1:
@@ -285,30 +333,70 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    rt.profile_enable(True)
-    rt.profile_collect()
-    dsea.runtime.stats["cg_iters"].clear()
-    l0 = rt.launch_count()
-    with ClockSampler(local_rank) as clk:
-        ms_total = timed(step_device, args.steps)
-    launches = rt.launch_count() - l0
-    prof = rt.profile_collect()
-    rt.profile_enable(False)
-    cg_iters = list(dsea.runtime.stats["cg_iters"])
-    clocks = clk.summary()
-    sec_per_solve = ms_total / 1e3 / args.steps
+    def measure(N_, k_, basis, steps, warmup, with_e2e=True, with_clocks=True):
+        """Times `steps` solves of (N_, k_) after `warmup`; returns the fields of a bench line."""
+        rt.set_option("basis_fp32", 1 if basis == "fp32" else 0)
+        model = dsea.TFIM(N_)
+        dsea.symeig.setDominantSparseSymeig(model.H, model.Hadjoint_to_gadjoint)
+        solve = dsea.symeig.DominantSparseSymeig.apply
+        n_loc = model.n_loc
+        g_host = torch.tensor([args.g], dtype=torch.float64).pin_memory()
+        out_host = torch.empty(2, dtype=torch.float64).pin_memory()
+        psi_host = torch.empty(n_loc, dtype=torch.float64).pin_memory() if with_e2e else None
+        g_dev = g_host.to(dev)
+        res = {}
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e_sec = ms_e2e / 1e3 / args.steps
+        def backward(E0, psi0):
+            if mode == "chiF":                                           # chiF.py:49-52 (shard-aware dot)
+                logF = torch.log(dsea.dot(psi0.detach(), psi0))
+                d1, = torch.autograd.grad(logF, model.g, create_graph=True)
+                d2, = torch.autograd.grad(d1, model.g)
+                return -d2
+            dE0, = torch.autograd.grad(E0, model.g)                      # E0.py:63
+            return dE0
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        def step_device():
+            model.g = g_dev.detach().requires_grad_(True)
+            E0, psi0 = solve(model.g, k_, model.dim, dev)
+            res["E0"], res["grad"], res["psi0"] = E0, backward(E0, psi0), psi0
+
+        def step_e2e():
+            model.g = g_host.to(dev, non_blocking=True).requires_grad_(True)
+            E0, psi0 = solve(model.g, k_, model.dim, dev)
+            grad = backward(E0, psi0)
+            out_host[0:1].copy_(E0.detach().reshape(1), non_blocking=True)
+            out_host[1:2].copy_(grad.detach().reshape(1), non_blocking=True)
+            psi_host.copy_(psi0.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(warmup):
+            step_device()
+        barrier()
+        rt.profile_enable(True)
+        rt.profile_collect()
+        dsea.runtime.stats["cg_iters"].clear()
+        l0 = rt.launch_count()
+        if with_clocks:
+            with ClockSampler(local_rank) as clk:
+                ms_total = timed(step_device, steps)
+            clocks = clk.summary()
+        else:
+            ms_total, clocks = timed(step_device, steps), None
+        launches = rt.launch_count() - l0
+        prof = rt.profile_collect()
+        rt.profile_enable(False)
+        out = {"N": N_, "k": k_, "n_loc": n_loc, "ms_total": ms_total, "steps": steps, "launches": launches,
+               "prof": prof, "clocks": clocks, "cg_iters": list(dsea.runtime.stats["cg_iters"]),
+               "E0": res["E0"].item(), "grad": res["grad"].item(),
+               "psi_norm_err": abs(dsea.dot(res["psi0"].detach(), res["psi0"].detach()).item() - 1.0)}
+        if with_e2e:
+            step_e2e()
+            out["e2e_s"] = timed(step_e2e, steps) / 1e3 / steps
+        res.clear()
+        del model
+        rt.set_option("basis_fp32", 0)
+        torch.cuda.empty_cache()
+        return out
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -316,51 +404,106 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
-    def kernel_line(name):
-        p = prof[name]
-        if p["launches"] == 0 or p["ms"] <= 0:
-            return None
-        if p["bytes"] <= 0:          # conditional (normally no-op) launches: report their time share only
-            return {"launches_per_step": p["launches"] / args.steps, "ms_per_step": p["ms"] / args.steps,
-                    "share_of_step": p["ms"] / ms_total}
-        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
-        return {"achieved": gbs, "frac": gbs / peak, "launches_per_step": p["launches"] / args.steps,
-                "ms_per_step": p["ms"] / args.steps, "share_of_step": p["ms"] / ms_total,
-                "algorithmic_bytes_per_step": p["bytes"] / args.steps}
+    def kernel_table(m):
+        prof, steps, ms_total = m["prof"], m["steps"], m["ms_total"]
+        table = {}
+        for name, p in prof.items():
+            if p["launches"] == 0 or p["ms"] <= 0:
+                continue
+            row = {"launches_per_step": p["launches"] / steps, "ms_per_step": p["ms"] / steps,
+                   "share_of_step": p["ms"] / ms_total}
+            if p["bytes"] > 0:
+                gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9
+                row.update(achieved=gbs, frac=gbs / peak, algorithmic_bytes_per_step=p["bytes"] / steps)
+            table[name] = row
+        table["unattributed_share_of_step"] = 1.0 - sum(r["share_of_step"] for r in table.values())
+        return table
 
-    kernels = {nm: kernel_line(nm) for nm in prof if kernel_line(nm)}
+    def check(m):
+        ex = tfim_exact(m["N"], args.g)
+        want = ex.chiF if mode == "chiF" else ex.dE0
+        return {"E0_rel_err": abs(m["E0"] - ex.E0) / abs(ex.E0),
+                ("chiF_rel_err" if mode == "chiF" else "dE0_rel_err"): abs(m["grad"] - want) / abs(want),
+                "psi_norm_err": m["psi_norm_err"]}
+
+    main_m = measure(N, k, args.basis, args.steps, args.warmup)
+    kernels = kernel_table(main_m)
+    sec_per_solve = main_m["ms_total"] / 1e3 / args.steps
+    n_loc = main_m["n_loc"]
+
     dom = kernels.get("reorth_update")
     roofline = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")       # from one `ncu --set full` capture
-    if dom and os.path.exists(tpath):
-        try:
-            recs = [r for kname, v in json.load(open(tpath)).items() if "reorth_update_kernel" in kname for r in v]
-            if recs:
-                ratio = sum(r["traffic_over_algorithmic"] for r in recs) / len(recs)
-                traffic = ratio * dom["algorithmic_bytes_per_step"] / dom["launches_per_step"]
-        except Exception:
-            traffic = None
-    if dom:
+    if dom and "achieved" in dom:
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by scripts/ncu_traffic.py from one `ncu --set full` capture
+        if os.path.exists(tpath):
+            try:
+                recs = [r for kname, v in json.load(open(tpath)).items() if "reorth_update_kernel" in kname for r in v]
+                if recs:
+                    ratio = sum(r["traffic_over_algorithmic"] for r in recs) / len(recs)
+                    traffic = ratio * dom["algorithmic_bytes_per_step"] / dom["launches_per_step"]
+                    traffic_src = "profiles/ncu_traffic.json (dram bytes / algorithmic bytes of the captured launches)"
+            except Exception:
+                traffic = None
         roofline = {"kernel": "reorth_update_kernel (r = u - Q c, pass 2 of full re-orthogonalisation)",
                     "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "achieved_bytes_per_launch": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"],
-                    "bytes_model": "8 n_loc (m + 2) per launch with m stored vectors (read Q[:, :m], read u, write r)",
+                    "bytes_model": "%d n_loc (m + 2) per launch with m stored vectors (read Q[:, :m], read u, write r)"
+                                   % (4 if args.basis == "fp32" else 8),
                     "share_of_step": dom["share_of_step"]}
 
     line = {"metric": METRIC, "value": sec_per_solve, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": False,
+            "warmup": args.warmup, "ms_per_step": main_m["ms_total"] / args.steps, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_sec, "unit": UNIT, "h2d_bytes_per_step": 8,
+            "e2e": {"value": main_m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": 8,
                     "d2h_bytes_per_step": 16 + 8 * n_loc},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
-            "cg_iterations_per_solve": cg_iters, "E0": results["E0"].item(), "dE0": results["dE0"].item()}
-    a = exact_tfim_energy(N, args.g)            # closed form, not the oracle: the product arm never imports oracle/
-    line["analytic_check"] = {"E0_rel_err": abs(line["E0"] - a[0]) / abs(a[0]),
-                              "dE0_rel_err": abs(line["dE0"] - a[1]) / abs(a[1])}
+            "gpu_launches": main_m["launches"], "clocks": main_m["clocks"], "roofline": roofline, "kernels": kernels,
+            "cg_iterations_per_solve": main_m["cg_iters"], "E0": main_m["E0"],
+            ("chiF" if mode == "chiF" else "dE0"): main_m["grad"], "analytic_check": check(main_m)}
+
+    if not args.no_extras:
+        if world == 1 and (N, k) != (SAMPLE_N, SAMPLE_K):
+            m2 = measure(SAMPLE_N, SAMPLE_K, "fp64", 5, 3, with_e2e=True, with_clocks=False)
+            line["pairs"] = {"config2": {"workload": workload_name(SAMPLE_N, SAMPLE_K, mode),
+                                         "ours_s_per_solve": m2["ms_total"] / 1e3 / 5, "ours_e2e_s_per_solve": m2["e2e_s"],
+                                         "gpu_launches_per_solve": m2["launches"] / 5, "analytic_check": check(m2)}}
+        if world > 1:
+            from dominantsparseeigenad_b200 import selfcheck
+            line["selfcheck"] = selfcheck.run()
+        head = {}
+        if world >= 4 and not args.spins:
+            for tag, (Nh, kh, basis) in {"config4_N28_k200": (28, 200, "fp64"),
+                                         "config5_N30_k200_fp32basis": (30, 200, "fp32")}.items():
+                if Nh == 30 and world < 8:
+                    continue
+                try:
+                    mh = measure(Nh, kh, basis, 2, 1, with_e2e=False, with_clocks=False)
+                    head[tag] = {"config": make_config(Nh, kh, basis), "value": mh["ms_total"] / 1e3 / 2, "unit": UNIT,
+                                 "steps": 2, "warmup": 1, "kernels": kernel_table(mh), "analytic_check": check(mh),
+                                 "cg_iterations_per_solve": mh["cg_iters"]}
+                except Exception as exc:                                 # capacity / option not available
+                    head[tag] = {"error": str(exc)[:300]}
+                    torch.cuda.empty_cache()
+        if head:
+            line["headline"] = head
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = run_cpu_arm(args, 1, 1, N, k)
+        cb = cpu_baseline_leg(args, mode)
+        line["cpu_baseline"] = cb
+        if "pairs" in line and cb["sample_workload"] == line["pairs"]["config2"]["workload"]:
+            line["pairs"]["config2"]["cpu_s_per_solve"] = cb["value"]
+            line["pairs"]["config2"]["cpu_kind"] = cb["kind"]
+        cached = os.path.join(ROOT, "profiles", "r2_reference_cpu_N24_k200.json")
+        if os.path.exists(cached):
+            try:
+                line["cpu_baseline"]["cached_full_size_run"] = json.load(open(cached))
+            except Exception:
+                pass
     if world > 1:
         dist.destroy_process_group()
     print(json.dumps(line))

@@ -304,6 +304,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "tfim_run_bits")) ctx->tfim_run_bits = (int)value;
     else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
+    else if (!strcmp(key, "basis_fp32")) ctx->basis_fp32 = (value != 0);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);

@@ -134,6 +134,7 @@ struct dsea_ctx {
     int tfim_tma = 1;                   // stage contiguous tiles with TMA bulk copies (UBLKCP + mbarrier) instead of LDGSTS
     int cg_check_every = 16;
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
+    int basis_fp32 = 0;                 // opt-in: Lanczos basis also kept as an fp32 shadow that the reorth passes stream
 };
 
 struct dsea_op {

@@ -53,7 +53,7 @@ def main():
 
     # ---- the sharded random start vector equals the single-GPU one (counter = global index)
     torch.manual_seed(77)
-    dsea.runtime._draw_counter = 0
+    dsea.runtime.reset_draw_counter()
     mine = dsea.runtime.start_vector(1 << 10, "lanczos").cpu()
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather_object(gathered, mine)
@@ -90,6 +90,10 @@ def main():
                 print("DIAG chiF", world, rt.p2p_enabled(), -d2.item(), achi, d1.item(),
                       dsea.runtime.stats["cg_iters"][-4:], flush=True)
     assert rel(-d2logF.item(), achi) < 1e-6, (-d2logF.item(), achi)
+    # the oracle-free identities bench.py asserts in every multi-GPU run (each spin bit, remote ones included)
+    from dominantsparseeigenad_b200 import selfcheck
+    sc = selfcheck.run()
+    assert sc["ok"], sc
     # every rank holds identical replicated scalars
     t = torch.tensor([E0.item(), dE0.item(), d2E0.item()], dtype=torch.float64, device=dev)
     lo, hi = t.clone(), t.clone()

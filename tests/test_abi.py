@@ -78,3 +78,16 @@ def test_no_cuda_means_loud_failure():
     from dominantsparseeigenad_b200 import runtime
     with pytest.raises(_lib.DseaError):
         runtime.context()
+
+
+def test_reference_import_alias_resolves_to_the_same_modules():
+    """`import DominantSparseEigenAD.symeig` must be the very module object of the implementation, so that the
+    reference's module-global rebinding protocol (symeig.py:66,87) works through the alias."""
+    import DominantSparseEigenAD.symeig as alias_symeig
+    from DominantSparseEigenAD.CG import CG_torch, CGSubspace          # noqa: F401
+    from DominantSparseEigenAD.Lanczos import Lanczos, symeigLanczos    # noqa: F401
+    from DominantSparseEigenAD.eig import DominantEig                   # noqa: F401
+    from DominantSparseEigenAD.symeig import DominantSymeig             # noqa: F401
+    import dominantsparseeigenad_b200 as impl
+    assert alias_symeig is impl.symeig
+    assert hasattr(alias_symeig, "setDominantSparseSymeig")

@@ -677,3 +677,123 @@ def test_error_behaviour(dsea):
     m = dsea.TFIM(6)
     with pytest.raises(ValueError):
         m.H(torch.zeros(64, dtype=F64, device="cuda"))       # g not set
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: production sweep kernels element-wise, config 3 at full size, non-convergence, CPU callers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [20, 22])
+def test_tfim_production_sweeps_elementwise_vs_oracle(dsea, orc, N):
+    """H, dH/dg and the adjoint at N = 20 / 22 with the DEFAULT tile plan, element by element against the
+    oracle's table-driven operator (TFIM.py:91-101 restated): at these sizes the second sweep takes the
+    persistent strided kernel and the first one the TMA-staged kernel, which the N <= 18 plan sweep
+    never reaches.  (The oracle's (2^N, N) int64 table is 168 MB / 738 MB here.)"""
+    rt = dsea.runtime.context()
+    rt.set_option("tfim_tile_bits", 13)
+    rt.set_option("tfim_run_bits", 0)
+    g = 0.75 + 0.01 * N
+    rng = np.random.default_rng(100 + N)
+    v, w = rng.standard_normal(1 << N), rng.standard_normal(1 << N)
+    o = orc.TFIMOracle(N, g)
+    m = dsea.TFIM(N)
+    m.g = cuda([g])
+    vd, wd = cuda(v), cuda(w)
+    want = o.H(torch.from_numpy(v)).numpy()
+    got = m.H(vd).cpu().numpy()
+    # every output is a sum of N + 1 terms of magnitude <= (N + g) max|v|: summation order differs, nothing else
+    assert np.abs(got - want).max() <= 4e-16 * (N + 1) * (N + g) * np.abs(v).max()
+    wantp = o.pHpg(torch.from_numpy(v)).numpy()
+    gotp = m.pHpg(vd).cpu().numpy()
+    assert np.abs(gotp - wantp).max() <= 4e-16 * N * N * np.abs(v).max()
+    want_adj = o.Hadjoint_to_gadjoint(torch.from_numpy(w), torch.from_numpy(v)).item()
+    assert rel(m.Hadjoint_to_gadjoint(wd, vd).item(), want_adj) < 1e-11
+    # shifted operator with the dot epilogue, as the CG loop calls it
+    u = m.matvec_raw(m.g, vd, cuda([-3.25]))
+    assert np.abs(u.cpu().numpy() - (want + 3.25 * v)).max() <= 4e-16 * (N + 2) * (N + g + 3.25) * np.abs(v).max()
+
+
+@pytest.mark.parametrize("g", [1.0, 1.5])
+def test_config3_chiF_and_d2E0_N24_k200(dsea, g):
+    """BASELINE config 3 at full size on one GPU: N = 24, k = 200, fp64 — E0, dE0/dg, d2E0/dg2 and the fidelity
+    susceptibility (three nested CG solves, CG.py:128-138) against the closed forms of BASELINE.md section 3
+    (chi_F = 17.25 / 0.534180712, d2E0/N = -1.174367973 / -0.183237299)."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    N, k = 24, 200
+    ex = tfim_exact(N, g)
+    E0, dE0, d2E0, psi0 = _tfim_E0_family(dsea, N, g, k)
+    assert rel(E0, ex.E0) < EVAL_RTOL
+    assert rel(dE0, ex.dE0) < GRAD_RTOL
+    assert rel(d2E0, ex.d2E0) < GRAD_RTOL
+    assert abs(dsea.dot(psi0, psi0).item() - 1.0) < 1e-12
+    del psi0
+    torch.cuda.empty_cache()
+    chif = _tfim_chif(dsea, N, g, k)
+    assert rel(chif, ex.chiF) < GRAD_RTOL
+    if g == 1.0:
+        assert rel(chif, 17.25) < GRAD_RTOL and rel(d2E0 / N, -1.174367973012996) < GRAD_RTOL
+    torch.cuda.empty_cache()
+
+
+def test_cg_reports_non_convergence(dsea):
+    """The reference returns silently after n iterations (CG.py:32).  The C ABI returns DSEA_ERR_NOCONV and the
+    Python layer turns it into a ConvergenceWarning while still handing back the last iterate."""
+    from dominantsparseeigenad_b200 import _lib
+    n = 300
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, n))
+    A = A @ A.T + 1e-3 * np.eye(n)                        # SPD, condition number ~1e6: 5 iterations cannot converge
+    b = rng.standard_normal(n)
+    op = dsea.DenseOperator(cuda(A))
+    with pytest.warns(_lib.ConvergenceWarning):
+        x = op.cg(None, None, cuda(b), cuda(np.zeros(n)), maxit=5)
+    assert dsea.runtime.stats["cg_iters"][-1] == 5 and torch.isfinite(x).all()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", _lib.ConvergenceWarning)
+        x = op.cg(None, None, cuda(b), cuda(np.zeros(n)))     # default cap n: converges, no warning
+    assert np.abs(A @ x.cpu().numpy() - b).max() < 1e-6
+
+
+def test_second_derivative_from_cpu_tensors(dsea, orc):
+    """CPU tensors in => CPU tensors out in every order of differentiation (the reference's documented contract,
+    CG.py docstring): d2E0/dg2 through DominantSymeig on a CPU matrix, against torch's own AD through eigh."""
+    N, g0 = 6, 1.1
+    o = orc.TFIMOracle(N, 1.0)
+    D = torch.diag(o.diag_elements.clone())
+    X = torch.zeros(o.dim, o.dim, dtype=F64)
+    cols = torch.arange(o.dim)
+    for i in range(N):
+        X[o.flips_basis[:, i], cols] -= 1.0
+
+    def second(fn):
+        g = torch.tensor([g0], dtype=F64, requires_grad=True)
+        E0 = fn(D + g * X)
+        dE0, = torch.autograd.grad(E0, g, create_graph=True)
+        d2E0, = torch.autograd.grad(dE0, g)
+        assert E0.device.type == "cpu" and dE0.device.type == "cpu" and d2E0.device.type == "cpu"
+        return E0.item(), dE0.item(), d2E0.item()
+
+    ours = second(lambda H: dsea.symeig.DominantSymeig.apply(H, 64)[0])
+    # eigh's AD divides by eigenvalue gaps; the even/odd sectors of H never mix, so use the analytic values too
+    aE0, adE0, ad2E0, _ = orc.tfim_analytic(N, g0)
+    assert rel(ours[0], aE0) < EVAL_RTOL and rel(ours[1], adE0) < GRAD_RTOL and rel(ours[2], ad2E0) < GRAD_RTOL
+
+
+def test_selfcheck_single_gpu(dsea):
+    """The identities bench.py asserts at P > 1 (character vectors per spin bit, <1,H1>, symmetry, small solve)
+    hold on one GPU as well — every bit class of the sweep plan (register, shared memory, strided, direct)."""
+    from dominantsparseeigenad_b200 import selfcheck
+    res = selfcheck.run(model=dsea.TFIM(23), small_N=14)
+    assert res["ok"], res
+
+
+def test_start_vector_stream_restarts_with_the_seed(dsea):
+    torch.manual_seed(4321)
+    a = dsea.runtime.start_vector(1000, "lanczos").clone()
+    b = dsea.runtime.start_vector(1000, "lanczos").clone()
+    torch.manual_seed(99)
+    c = dsea.runtime.start_vector(1000, "lanczos").clone()
+    torch.manual_seed(4321)
+    a2 = dsea.runtime.start_vector(1000, "lanczos").clone()
+    b2 = dsea.runtime.start_vector(1000, "lanczos").clone()
+    assert torch.equal(a, a2) and torch.equal(b, b2) and not torch.equal(a, b) and not torch.equal(a, c)
