@@ -33,7 +33,7 @@ __global__ void cg_setup_kernel(double* scal, double eps, double maxit) {
 // r = b - Ax ; d = r ; partial r.r
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(const double* __restrict__ b, const double* __restrict__ Ax, double* __restrict__ r,
-               double* __restrict__ d, int64_t n, double* __restrict__ partials) {
+               double* __restrict__ d, int64_t n, double* __restrict__ partials, const PeerPtrs peers) {
     __shared__ double red[32];
     double s = 0.0;
     const int64_t n2 = n >> 1;
@@ -43,12 +43,14 @@ cg_init_kernel(const double* __restrict__ b, const double* __restrict__ Ax, doub
         const double2 rv = make_double2(bv.x - av.x, bv.y - av.y);
         stg2(r + 2 * i, rv);
         stg2(d + 2 * i, rv);
+        for (int pj = 0; pj < peers.n; ++pj) stg2(peers.p[pj] + 2 * i, rv);      // fused exchange of d (NVLink stores)
         s += rv.x * rv.x + rv.y * rv.y;
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const double rv = b[n - 1] - Ax[n - 1];
         r[n - 1] = rv;
         d[n - 1] = rv;
+        for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][n - 1] = rv;
         s += rv * rv;
     }
     s = block_sum(s, red);
@@ -116,7 +118,8 @@ __global__ void cg_scalar_kernel(double* scal) {
 
 // d = r + beta d                                                                   (CG.py:39)
 __global__ void __launch_bounds__(kCgThreads)
-cg_update_d_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t n, const double* __restrict__ scal) {
+cg_update_d_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t n, const double* __restrict__ scal,
+                   const PeerPtrs peers) {
     if (scal[S_DONE] != 0.0) return;
     const double beta = scal[S_BETA];
     const int64_t n2 = n >> 1;
@@ -127,8 +130,13 @@ cg_update_d_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t
         dv.x = rv.x + beta * dv.x;
         dv.y = rv.y + beta * dv.y;
         stg2(d + 2 * i, dv);
+        for (int pj = 0; pj < peers.n; ++pj) stg2(peers.p[pj] + 2 * i, dv);      // fused exchange: the next matvec's remote shards
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) d[n - 1] = r[n - 1] + beta * d[n - 1];
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double dv = r[n - 1] + beta * d[n - 1];
+        d[n - 1] = dv;
+        for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][n - 1] = dv;
+    }
 }
 
 int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st) {
@@ -138,9 +146,13 @@ int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st) {
     return DSEA_OK;
 }
 
-int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st) {
+int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st,
+            const PeerPtrs* peers) {
     const int grid = cg_grid(ctx, n);
-    cg_init_kernel<<<grid, kCgThreads, 0, st>>>(b, Ax, r, d, n, ctx->partials);
+    PeerPtrs pp;
+    pp.n = 0;
+    if (peers) pp = *peers;
+    cg_init_kernel<<<grid, kCgThreads, 0, st>>>(b, Ax, r, d, n, ctx->partials, pp);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR, st));
@@ -151,8 +163,12 @@ int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double*
 }
 
 // one iteration AFTER Ad and d.Ad (scal[S_DAD]) are available
-int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st) {
+int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st,
+               const PeerPtrs* peers) {
     const int grid = cg_grid(ctx, n);
+    PeerPtrs pp;
+    pp.n = 0;
+    if (peers) pp = *peers;
     int tok = prof_begin(ctx, PK_CG_UPDATE, 48.0 * (double)n, st);
     cg_update_xr_kernel<<<grid, kCgThreads, 0, st>>>(x, r, d, Ad, n, ctx->scal, ctx->partials);
     prof_end(ctx, tok, st);
@@ -161,8 +177,8 @@ int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const 
     DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
     cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal);
     prof_guard_next_phase(ctx);
-    tok = prof_begin(ctx, PK_CG_UPDATE, 24.0 * (double)n, st);
-    cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal);
+    tok = prof_begin(ctx, PK_CG_UPDATE, (24.0 + 8.0 * pp.n) * (double)n, st);
+    cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx, 2);
     DSEA_CUDA(cudaGetLastError());

@@ -132,6 +132,13 @@ struct dsea_ctx {
     int tfim_run_bits = 0;              // 0 = auto
     int tfim_pipeline = 1;              // persistent double-buffered sweep kernel for full 2^13 tiles
     int tfim_tma = 1;                   // stage contiguous tiles with TMA bulk copies (UBLKCP + mbarrier) instead of LDGSTS
+    int tfim_pipe_threads = 512;        // 512: 8 pairs / thread (4 register bits); 256: 16 pairs / thread (5 register bits)
+    int tfim_direct = 1;                // top local bits beyond two sweeps by direct (L2-served) loads instead of a third sweep
+    int tfim_fuse_scale = 1;            // fold the Lanczos normalisation q = r / beta into the first matvec sweep
+    int tfim_l2_prefetch = 1;           // prefetch.global.L2 the next tile's epilogue operands
+    int tfim_pipe_adjoint = 1;          // adjoint contraction (K6) through the pipelined kernel
+    int tfim_pipe_remote = 1;           // last sweep of a sharded matvec through the pipelined kernel
+    int cg_fuse_push = 1;               // CG direction update stores d into the partners' arenas
     int cg_check_every = 16;
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
     int basis_fp32 = 0;                 // opt-in: Lanczos basis also kept as an fp32 shadow that the reorth passes stream
@@ -158,11 +165,19 @@ namespace dsea {
 
 // ---- internal kernels' host launchers (each returns a DSEA status) ----------------------------
 // tfim.cu
-// `prepushed`: the input shard already sits in the partners' arenas (written by the producing kernel),
-// scaled there by 1 / *remote_scale^-1, i.e. the remote terms are multiplied by *remote_scale.
+// `exchange` (sharded runs with the peer arena): XCH_PUSH = publish v with barrier + push kernel + barrier;
+// XCH_PREPUSHED = the kernel that produced v already stored it into the partners' arenas and a collective has
+// completed since (Lanczos: reorth pass 2 followed by the beta^2 reduction); XCH_PREPUSHED_BARRIER = stored by the
+// producer, but no collective followed: one barrier is issued before the last sweep (CG direction update).
+// The arena copy may be unscaled: the remote terms are multiplied by *remote_scale.
+// `in_scale` / `q_out`: the logical input is (*in_scale) * v and is also written to q_out (fused normalisation of
+// the new Lanczos vector); only when tfim_can_fuse_scale().
+enum { XCH_PUSH = 0, XCH_PREPUSHED = 1, XCH_PREPUSHED_BARRIER = 2 };
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
                double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st,
-               bool prepushed = false, const double* remote_scale = nullptr);
+               int exchange = XCH_PUSH, const double* remote_scale = nullptr, const double* in_scale = nullptr,
+               double* q_out = nullptr);
+bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op);
 int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st);
 int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
                  double* work, cudaStream_t st);
@@ -193,8 +208,11 @@ int tridiag_extreme(dsea_ctx* ctx, int k, int which, const double* alpha, const 
                     double* evals, double* y_min, double* y_max, cudaStream_t st);
 // cg.cu
 int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st);
-int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st);
-int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st);
+// `peers`: when non-null the kernels that write the search direction d also store it into the partners' arenas
+int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st,
+            const PeerPtrs* peers = nullptr);
+int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st,
+               const PeerPtrs* peers = nullptr);
 // comm.cu
 int comm_init(dsea_ctx* ctx, const void* id);
 int comm_destroy(dsea_ctx* ctx);

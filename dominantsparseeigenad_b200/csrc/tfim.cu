@@ -7,27 +7,38 @@
 // No index table exists: the reference's (2^N, N) int64 table (60 GB at N=28) is replaced by bit
 // arithmetic on the global index (rank << L) | s_loc.
 //
-// Memory plan.  A CTA stages a TILE of 2^T doubles in shared memory and serves every flip whose
-// bit lies inside the tile from there, so each vector element is read from HBM once per SWEEP:
+// Memory plan.  A CTA stages a TILE of 2^T doubles in shared memory and serves every flip whose bit lies
+// inside the tile from there, so each vector element is read from HBM once per SWEEP:
 //   sweep 0 : tile = 2^T contiguous doubles            -> handles spin bits [0, T)
 //   sweep j : tile = 2^c contiguous x 2^h strided runs -> handles h spin bits starting at `hshift`
-//             (run stride 2^hshift doubles; c >= 2 keeps every global access a full 32 B sector,
-//             c >= 4 a full 128 B line)
+//             (run stride 2^hshift doubles).  Runs are at least 2^4 doubles = one 128-byte line, so a warp's
+//             16-byte accesses touch 4 lines per instruction exactly like a contiguous stream (round 1 used
+//             32-byte runs: 16 lines per instruction, which made the sweep L1TEX-wavefront bound).
+//   direct  : with 13-bit tiles two sweeps reach 13 + 9 = 22 local bits.  Up to kMaxDirect further (top)
+//             local bits are NOT given a third sweep (24 more bytes per element of HBM traffic); the last
+//             sweep reads the partner elements v[s ^ (1<<b)] straight from global memory.  The tile order
+//             puts the 2^ndirect tiles that are each other's partners on neighbouring CTAs in the same
+//             iteration, so those reads are served by L2 (each tile is fetched from HBM once, by its owner).
 //   top log2(world) bits : the shard of rank ^ (1<<j) sits in slot j of this rank's peer arena, stored
-//             there over NVLink by the kernel that produced it (reorth pass 2, or push_kernel); the
-//             last sweep adds the slots.  Fallback: grouped ncclSend/ncclRecv on a side stream,
-//             overlapped with the local sweeps.
-// HBM bytes per element: 16 (first sweep: read v, write u) + 24 per extra sweep (read v, read u,
-// write u) + 8 per remote bit.  The dot-product epilogue (v.u for CG, or w.u) rides on the last sweep.
+//             there over NVLink by the kernel that produced it (reorth pass 2, the CG direction update, or
+//             push_kernel); the last sweep adds the slots.  Fallback: grouped ncclSend/ncclRecv on a side
+//             stream, overlapped with the local sweeps.
+// HBM bytes per element: 16 (first sweep: read v, write u) + 24 per extra sweep (read v, read u, write u)
+// + 8 per remote bit.  The dot-product epilogue (v.u for CG, or w.u) rides on the last sweep.
+// Fused normalisation (K3): the first sweep can take its input as in_scale * v and write the scaled vector
+// back (q = r / beta), which removes the separate 16 B/element normalisation pass of every Lanczos step.
 #include "common.cuh"
 
 namespace dsea {
+
+constexpr int kMaxDirect = 5;
 
 struct Sweep {
     int T;        // tile bits
     int c;        // contiguous low bits of the tile
     int hshift;   // global bit position of tile bit c
     int b0;       // first tile bit this sweep is responsible for
+    int ndirect;  // local bits above the tile's strided range served by direct global loads
 };
 
 struct SweepParams {
@@ -37,6 +48,8 @@ struct SweepParams {
     const double* w;        // dot partner (may alias v); nullptr = no dot
     const double* g;
     const double* shift;
+    const double* in_scale; // MODE_FIRST: the logical input is (*in_scale) * v   (nullptr = 1)
+    double* q_out;          // MODE_FIRST: if non-null the scaled input is written here (may alias v)
     const double* recv;     // nrecv buffers, `recv_stride` doubles apart (NCCL recv buffers or the IPC arena)
     const double* remote_scale;   // device scalar multiplying the remote terms (nullptr = 1)
     uint64_t recv_stride;
@@ -47,8 +60,12 @@ struct SweepParams {
     uint64_t ntiles;
     int nrecv;
     int N, T, c, hshift, b0;
+    int upbits;             // address bits above the tile's strided range: L - (hshift + T - c)
+    int ndirect;            // 0 or upbits
+    int fast_up;            // 1: the tile index's LOW bits select the upper address bits (partner tiles adjacent)
     int no_diag;            // 1: drop the diagonal (u = -g * flip sum), used for dH/dg
     int use_tma;            // 1: stage contiguous tiles with cp.async.bulk + mbarrier (pipelined kernel only)
+    int l2_prefetch;        // 1: prefetch.global.L2 the next tile's epilogue operands
 };
 
 __device__ __forceinline__ double tfim_diag_dev(uint64_t s, int N, uint64_t mask) {
@@ -56,9 +73,24 @@ __device__ __forceinline__ double tfim_diag_dev(uint64_t s, int N, uint64_t mask
     return -(double)(N - 2 * __popcll(s ^ rot));
 }
 
+// tile index -> offset of the tile's element 0
+__device__ __forceinline__ uint64_t tile_base(const SweepParams& p, uint64_t t) {
+    const int midbits = p.hshift - p.c;
+    uint64_t t_mid, t_up;
+    if (p.fast_up) {
+        t_up = t & ((1ull << p.upbits) - 1ull);
+        t_mid = t >> p.upbits;
+    } else {
+        t_mid = t & ((1ull << midbits) - 1ull);
+        t_up = t >> midbits;
+    }
+    return (t_mid << p.c) | (t_up << (p.hshift + p.T - p.c));
+}
+
 constexpr int kSweepThreads = 512;
 enum { MODE_FIRST = 0, MODE_ACCUM = 1, MODE_ADJ = 2 };
 
+// ---- generic sweep: any tile size / plan; 2 CTAs per SM, one pair per thread at a time ---------------------
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(16) double tile[];
@@ -67,7 +99,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
     const int T = p.T, c = p.c;
     const uint32_t cmask = (1u << c) - 1u;
     const int half = 1 << (T - 1);
-    const int midbits = p.hshift - c;
+    const int dpos = p.hshift + T - c;
     const uint64_t nmask = (p.N >= 64) ? ~0ull : ((1ull << p.N) - 1ull);
     const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
     const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
@@ -75,8 +107,7 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
     double part = 0.0;
 
     for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        const uint64_t t_mid = t & ((1ull << midbits) - 1ull), t_up = t >> midbits;
-        const uint64_t base = (t_mid << c) | (t_up << (p.hshift + T - c));
+        const uint64_t base = tile_base(p, t);
         // ---- stage the tile (coalesced 16 B loads; runs of 2^c doubles) ----
 #pragma unroll 4
         for (int e2 = threadIdx.x; e2 < half; e2 += kSweepThreads) {
@@ -96,6 +127,11 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
             if (b == 0) { a0 = x.y; a1 = x.x; b = 1; }        // bit 0: the pair partner
             for (; b < T; ++b) {
                 const double2 y = *reinterpret_cast<const double2*>(&tile[e ^ (1u << b)]);
+                a0 += y.x;
+                a1 += y.y;
+            }
+            for (int d = 0; d < p.ndirect; ++d) {               // top local bits: partner tiles, through L2
+                const double2 y = ldg2(p.v + (gi ^ (1ull << (dpos + d))));
                 a0 += y.x;
                 a1 += y.y;
             }
@@ -141,15 +177,12 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
 }
 
 // ---- fast path: persistent, double-buffered, register-blocked sweep for full 2^13 tiles -------------
-// One CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Tile i+1 is fetched with cp.async
-// (LDGSTS, 16 B) into the second 64 KB buffer while tile i is being reduced, so the HBM stream never
-// waits for the shared-memory phase.  A thread owns 8 pairs = 16 amplitudes whose tile bits {0,10,11,12}
-// vary: flips of those four bits are register moves; only tile bits 1..9 are served by shared memory
-// (9 conflict-free LDS.128 per pair instead of 12), which brings the crossbar traffic of a tile below
-// its HBM time.
+// One CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Tile i+1 is fetched asynchronously into
+// the second 64 KB buffer while tile i is being reduced: contiguous tiles by TMA bulk copies (UBLKCP, one
+// elected thread, completion on an mbarrier), strided tiles by cp.async (LDGSTS, 16 B, runs >= 128 B).
+// A thread owns PAIRS = 4096 / THREADS pairs whose tile bit 0 and top log2(PAIRS) tile bits vary: flips of
+// those bits are register moves; only the remaining tile bits are served by conflict-free LDS.128.
 constexpr int kPipeT = 13;
-constexpr int kPipeThreads = 512;
-constexpr int kPipePairs = (1 << (kPipeT - 1)) / kPipeThreads;   // 8
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -158,6 +191,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: used for CONTIGUOUS tiles, where one
 // elected thread moves the whole 64 KB tile with four instructions instead of 4096 LDGSTS.
@@ -187,14 +221,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  : "memory");
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
-    extern __shared__ __align__(128) double bufs[];              // 2 x 2^13 doubles
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
+    constexpr int T = kPipeT;
+    constexpr int PAIRS = (1 << (T - 1)) / THREADS;            // 8 (512 threads) or 16 (256 threads)
+    constexpr int RBITS = (PAIRS == 8) ? 3 : 4;                // register-resident top tile bits
+    constexpr int RB0 = T - RBITS;                             // first of them: tile bit 10 or 9
+    extern __shared__ __align__(128) double bufs[];            // 2 x 2^13 doubles
     __shared__ double red[32];
     __shared__ __align__(8) uint64_t mbar[2];
     if (p.guard && *p.guard != 0.0) return;
-    constexpr int T = kPipeT;
-    const bool tma = p.use_tma != 0;                             // contiguous tiles only (first sweep)
+    const bool tma = p.use_tma != 0;                           // contiguous tiles only (first sweep)
     uint32_t phase[2] = {0u, 0u};
     if (tma) {
         if (threadIdx.x == 0) {
@@ -206,27 +243,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
     }
     const int c = p.c;
     const uint32_t cmask = (1u << c) - 1u;
-    const int midbits = p.hshift - c;
+    const int dpos = p.hshift + T - c;
     const uint64_t nmask = (p.N >= 64) ? ~0ull : ((1ull << p.N) - 1ull);
     const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
     const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
+    const double scl = (MODE == MODE_FIRST && p.in_scale) ? *p.in_scale : 1.0;
     const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
     const int bstart = p.b0 > 1 ? p.b0 : 1;
     double part = 0.0;
 
-    uint32_t e[kPipePairs];                                      // tile offsets of this thread's pairs
+    uint32_t e[PAIRS];                                         // tile offsets of this thread's pairs
 #pragma unroll
-    for (int j = 0; j < kPipePairs; ++j) e[j] = 2u * (threadIdx.x + kPipeThreads * j);
+    for (int j = 0; j < PAIRS; ++j) e[j] = 2u * (threadIdx.x + THREADS * j);
 
-    auto tile_base = [&](uint64_t t) -> uint64_t {
-        const uint64_t t_mid = t & ((1ull << midbits) - 1ull), t_up = t >> midbits;
-        return (t_mid << c) | (t_up << (p.hshift + T - c));
-    };
     auto gidx = [&](uint64_t base, uint32_t ee) -> uint64_t {
         return base | (ee & cmask) | ((uint64_t)(ee >> c) << p.hshift);
     };
     auto prefetch = [&](uint64_t t, double* buf, int st) {
-        const uint64_t base = tile_base(t);
+        const uint64_t base = tile_base(p, t);
         if (tma) {
             if (threadIdx.x == 0) {
                 constexpr uint32_t kChunk = (uint32_t)(sizeof(double) << T) / 4;           // 16 KB
@@ -235,11 +269,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
                 for (int q = 0; q < 4; ++q)
                     tma_bulk_g2s(buf + q * (kChunk / 8), p.v + base + q * (kChunk / 8), kChunk, &mbar[st]);
             }
-            return;
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < kPipePairs; ++j) cp_async16(buf + e[j], p.v + gidx(base, e[j]));
-        cp_async_commit();
+            for (int j = 0; j < PAIRS; ++j) cp_async16(buf + e[j], p.v + gidx(base, e[j]));
+            cp_async_commit();
+        }
+        if (p.l2_prefetch && c >= 4) {                          // the next tile's epilogue operands, one 128 B line each
+            for (uint32_t l = threadIdx.x; l < (1u << (T - 4)); l += THREADS) {
+                const uint64_t gl = gidx(base, 16u * l);
+                if (MODE == MODE_ACCUM) prefetch_l2(p.uin + gl);
+                for (int d = 0; d < p.ndirect; ++d) prefetch_l2(p.v + (gl ^ (1ull << (dpos + d))));
+                for (int q = 0; q < p.nrecv; ++q) prefetch_l2(p.recv + (uint64_t)q * p.recv_stride + gl);
+                if (p.w && p.w != p.v) prefetch_l2(p.w + gl);
+            }
+        }
     };
 
     uint64_t t = blockIdx.x;
@@ -248,13 +291,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
     for (; t < p.ntiles; t += gridDim.x, stage ^= 1) {
         const double* buf = bufs + ((size_t)stage << T);
         const uint64_t tn = t + gridDim.x;
-        const uint64_t base = tile_base(t);
+        const uint64_t base = tile_base(p, t);
         if (tn < p.ntiles) prefetch(tn, bufs + ((size_t)(stage ^ 1) << T), stage ^ 1);
-        double2 ui[kPipePairs];
-        if (MODE == MODE_ACCUM) {                                 // issue these HBM loads before waiting
-#pragma unroll
-            for (int j = 0; j < kPipePairs; ++j) ui[j] = ldg2(p.uin + gidx(base, e[j]));
-        }
         if (tma) {
             mbar_wait(&mbar[stage], phase[stage]);                // the bulk copy's bytes have landed
             phase[stage] ^= 1u;
@@ -263,59 +301,98 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
             __syncthreads();
         }
 
-        double2 x[kPipePairs], a[kPipePairs];
+        double2 x[PAIRS], a[PAIRS];
 #pragma unroll
-        for (int j = 0; j < kPipePairs; ++j) x[j] = *reinterpret_cast<const double2*>(buf + e[j]);
+        for (int j = 0; j < PAIRS; ++j) x[j] = *reinterpret_cast<const double2*>(buf + e[j]);
 #pragma unroll
-        for (int j = 0; j < kPipePairs; ++j) {                    // register-resident flips
-            a[j] = (p.b0 == 0) ? make_double2(x[j].y, x[j].x) : make_double2(0.0, 0.0);   // tile bit 0
+        for (int j = 0; j < PAIRS; ++j)                           // tile bit 0: the pair partner
+            a[j] = (p.b0 == 0) ? make_double2(x[j].y, x[j].x) : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int jb = 0; jb < 3; ++jb) {                      // tile bits 10, 11, 12
-                a[j].x += x[j ^ (1 << jb)].x;
-                a[j].y += x[j ^ (1 << jb)].y;
+        for (int jb = 0; jb < RBITS; ++jb) {                      // register-resident flips: tile bits RB0 .. 12
+            if (RB0 + jb >= p.b0) {
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    a[j].x += x[j ^ (1 << jb)].x;
+                    a[j].y += x[j ^ (1 << jb)].y;
+                }
             }
         }
-        for (int b = bstart; b < 10; ++b) {                       // tile bits 1..9 from shared memory
+        for (int b = bstart; b < RB0; ++b) {                      // the other tile bits from shared memory
 #pragma unroll
-            for (int j = 0; j < kPipePairs; ++j) {
+            for (int j = 0; j < PAIRS; ++j) {
                 const double2 y = *reinterpret_cast<const double2*>(buf + (e[j] ^ (1u << b)));
                 a[j].x += y.x;
                 a[j].y += y.y;
             }
         }
+        // ---- epilogue: operands that live in global memory (L2-resident when prefetched) ----
+        for (int d = 0; d < p.ndirect; ++d) {                     // top local bits: partner tiles
+            const uint64_t dbit = 1ull << (dpos + d);
+            double2 y[PAIRS];
 #pragma unroll
-        for (int j = 0; j < kPipePairs; ++j) {
-            const uint64_t gi = gidx(base, e[j]);
-            double a0 = a[j].x, a1 = a[j].y;
-            if (p.nrecv > 0) {                                    // top (remote) spin bits
-                double r0 = 0.0, r1 = 0.0;
-                for (int q = 0; q < p.nrecv; ++q) {
-                    const double2 y = ldg2(p.recv + (uint64_t)q * p.recv_stride + gi);
-                    r0 += y.x;
-                    r1 += y.y;
-                }
-                a0 += rscale * r0;
-                a1 += rscale * r1;
+            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(p.v + (gidx(base, e[j]) ^ dbit));
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) {
+                a[j].x += y[j].x;
+                a[j].y += y[j].y;
             }
-            if (MODE == MODE_ADJ) {
-                const double2 wv = ldg2(p.w + gi);
-                part -= wv.x * a0 + wv.y * a1;
-            } else {
-                double2 o;
-                if (MODE == MODE_FIRST) {
-                    const uint64_t s = p.rank_off | gi;
+        }
+        for (int q = 0; q < p.nrecv; ++q) {                       // top (remote) spin bits
+            const double* slot = p.recv + (uint64_t)q * p.recv_stride;
+            double2 y[PAIRS];
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(slot + gidx(base, e[j]));
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) {
+                a[j].x += rscale * y[j].x;
+                a[j].y += rscale * y[j].y;
+            }
+        }
+        if (MODE == MODE_ADJ) {
+            double2 wv[PAIRS];
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, e[j]));
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) part -= wv[j].x * a[j].x + wv[j].y * a[j].y;
+        } else {
+            double2 o[PAIRS];
+            if (MODE == MODE_FIRST) {
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    const uint64_t s = p.rank_off | gidx(base, e[j]);
                     const double d0 = p.no_diag ? 0.0 : tfim_diag_dev(s, p.N, nmask);
                     const double d1 = p.no_diag ? 0.0 : tfim_diag_dev(s | 1ull, p.N, nmask);
-                    o.x = (d0 - shift) * x[j].x - g * a0;
-                    o.y = (d1 - shift) * x[j].y - g * a1;
-                } else {
-                    o.x = ui[j].x - g * a0;
-                    o.y = ui[j].y - g * a1;
+                    o[j].x = scl * ((d0 - shift) * x[j].x - g * a[j].x);
+                    o[j].y = scl * ((d1 - shift) * x[j].y - g * a[j].y);
+                    x[j].x *= scl;                                // the logical input (for q_out and the dot)
+                    x[j].y *= scl;
                 }
-                stg2(p.uout + gi, o);
-                if (p.w) {
-                    const double2 wv = (p.w == p.v) ? x[j] : ldg2(p.w + gi);
-                    part += wv.x * o.x + wv.y * o.y;
+                if (p.q_out) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) stg2(p.q_out + gidx(base, e[j]), x[j]);
+                }
+            } else {
+                double2 ui[PAIRS];
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) ui[j] = ldg2(p.uin + gidx(base, e[j]));
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    o[j].x = ui[j].x - g * a[j].x;
+                    o[j].y = ui[j].y - g * a[j].y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) stg2(p.uout + gidx(base, e[j]), o[j]);
+            if (p.w) {
+                if (p.w == p.v) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) part += x[j].x * o[j].x + x[j].y * o[j].y;
+                } else {
+                    double2 wv[PAIRS];
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, e[j]));
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) part += wv[j].x * o[j].x + wv[j].y * o[j].y;
                 }
             }
         }
@@ -328,50 +405,73 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tfim_sweep_pipe_kernel(const 
 }
 
 // Sweep schedule for L local bits with tiles of at most Tmax bits.
-static int plan_sweeps(int L, int Tmax, int run_bits, Sweep* out) {
+//   run_bits > 0 : every strided sweep uses runs of exactly 2^run_bits doubles (tests / tuning), no direct bits;
+//   run_bits = 0 : automatic.  Runs are at least `cmin` bits long (4 = one 128-byte line for production tiles, 2 for
+//                  the tiny tiles the tests use); the fewest sweeps that reach every bit are used, each with the
+//                  longest runs that keep that count.  With `allow_direct`, up to kMaxDirect top bits left over
+//                  by TWO sweeps become direct loads of the last sweep instead of a third sweep.
+static int plan_sweeps(int L, int Tmax, int run_bits, bool allow_direct, Sweep* out) {
     int n = 0;
     const int T1 = L < Tmax ? L : Tmax;
-    out[n++] = Sweep{T1, T1, T1, 0};
+    out[n++] = Sweep{T1, T1, T1, 0, 0};
     int rem = L - T1, pos = T1;
-    if (rem > 0) {
+    if (rem <= 0) return n;
+    if (run_bits > 0) {
         int c = run_bits;
-        if (c <= 0) {
-            // fewest sweeps subject to c >= 2 (32 B sectors); then the longest runs that keep that count
-            const int nmin = (rem + (Tmax - 2) - 1) / (Tmax - 2);
-            c = 2;
-            for (int cc = 3; cc <= 8 && cc < Tmax; ++cc)
-                if ((rem + (Tmax - cc) - 1) / (Tmax - cc) == nmin) c = cc;
-        }
         if (c > T1) c = T1;
         if (c > Tmax - 1) c = Tmax - 1;      // every strided sweep must handle at least one new bit
         if (c < 1) c = 1;
         int nsw = (rem + (Tmax - c) - 1) / (Tmax - c);
         while (rem > 0 && n < kMaxSweeps) {
             const int h = (rem + nsw - 1) / nsw;
-            out[n++] = Sweep{c + h, c, pos, c};
+            out[n++] = Sweep{c + h, c, pos, c, 0};
             pos += h;
             rem -= h;
             --nsw;
         }
-        if (rem > 0) return -1;
+        return rem > 0 ? -1 : n;
     }
-    return n;
+    int cmin = Tmax >= 10 ? 4 : 2;
+    if (cmin > Tmax - 1) cmin = Tmax - 1;
+    if (cmin < 1) cmin = 1;
+    const int hmax = Tmax - cmin;
+    if (allow_direct && Tmax >= 10 && rem > hmax && rem - hmax <= kMaxDirect) {
+        out[n++] = Sweep{Tmax, cmin, pos, cmin, rem - hmax};
+        return n;
+    }
+    int nsw = (rem + hmax - 1) / hmax;
+    while (rem > 0 && n < kMaxSweeps) {
+        const int h = (rem + nsw - 1) / nsw;
+        int c = Tmax - h;                    // longest runs that still fit h new bits into one tile
+        if (c > T1) c = T1;
+        out[n++] = Sweep{c + h, c, pos, c, 0};
+        pos += h;
+        rem -= h;
+        --nsw;
+    }
+    return rem > 0 ? -1 : n;
+}
+
+template <int MODE, int THREADS>
+static int launch_pipe(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream_t st) {
+    const size_t smem2 = (sizeof(double) << kPipeT) * 2;
+    static bool done = false;
+    if (!done) {
+        DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_pipe_kernel<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem2));
+        done = true;
+    }
+    tfim_sweep_pipe_kernel<MODE, THREADS><<<grid, THREADS, smem2, st>>>(p);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    return DSEA_OK;
 }
 
 template <int MODE>
 static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, bool pipe, cudaStream_t st) {
     if (pipe) {
-        const size_t smem2 = (sizeof(double) << kPipeT) * 2;
-        static bool pipe_attr_done[3] = {false, false, false};
-        if (!pipe_attr_done[MODE]) {
-            DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem2));
-            pipe_attr_done[MODE] = true;
-        }
-        tfim_sweep_pipe_kernel<MODE><<<grid, kPipeThreads, smem2, st>>>(p);
-        count_launch(ctx);
-        DSEA_CUDA(cudaGetLastError());
-        return DSEA_OK;
+        if (ctx->tfim_pipe_threads == 256) return launch_pipe<MODE, 256>(ctx, p, grid, st);
+        return launch_pipe<MODE, 512>(ctx, p, grid, st);
     }
     const size_t smem = sizeof(double) << p.T;
     static bool attr_done[3] = {false, false, false};
@@ -386,28 +486,50 @@ static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, bool pipe
     return DSEA_OK;
 }
 
-// Shared driver: mode_adj=false -> u = H v (- shift v), optional dot with `dotw`;
+static inline int clamp_tile_bits(int Tmax) { return Tmax > 14 ? 14 : (Tmax < 3 ? 3 : Tmax); }
+
+static inline bool pipe_eligible(const dsea_ctx* ctx, const Sweep& s, uint64_t ntiles) {
+    return ctx->tfim_pipeline && s.T == kPipeT && ntiles >= 2;
+}
+
+// True when the FIRST sweep of this operator runs in the pipelined kernel, i.e. tfim_apply can take
+// `in_scale` / `q_out` (fused normalisation of the Lanczos vector).
+bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op) {
+    Sweep sw[kMaxSweeps];
+    const int ns = plan_sweeps(op->L, clamp_tile_bits(ctx->tfim_tile_bits), ctx->tfim_run_bits, ctx->tfim_direct != 0, sw);
+    return ns > 0 && ctx->tfim_fuse_scale && pipe_eligible(ctx, sw[0], 1ull << (op->L - sw[0].T));
+}
+
+// Shared driver: mode_adj=false -> u = H (in_scale v) (- shift ...), optional dot with `dotw`;
 //                mode_adj=true  -> out = -sum_s w[s] * sum_i v[s^(1<<i)].
+// `exchange`: how the top-bit shards of v reach this rank when the peer arena is in use:
+//   XCH_PUSH       nobody has published v yet: barrier, push kernel, barrier (all attributed to PK_EXCHANGE);
+//   XCH_PREPUSHED  the kernel that produced v stored it into the partners' arenas and a collective has completed since;
+//   XCH_PREPUSHED_BARRIER  as above but no collective followed the producer: one barrier before the last sweep.
 static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const double* g, const double* shift,
-                    const double* v, double* u, const double* w, double* dot_out, double* work,
-                    cudaStream_t st, bool prepushed = false, const double* remote_scale = nullptr) {
+                    const double* v, double* u, const double* w, double* dot_out, double* work, cudaStream_t st,
+                    int exchange, const double* remote_scale, const double* in_scale, double* q_out) {
     Sweep sw[kMaxSweeps];
     const int L = op->L;
-    int Tmax = ctx->tfim_tile_bits;
-    if (Tmax > 14) Tmax = 14;
-    if (Tmax < 3) Tmax = 3;
-    const int ns = plan_sweeps(L, Tmax, ctx->tfim_run_bits, sw);
+    const int Tmax = clamp_tile_bits(ctx->tfim_tile_bits);
+    const int ns = plan_sweeps(L, Tmax, ctx->tfim_run_bits, ctx->tfim_direct != 0, sw);
     DSEA_ARG(ns > 0, "TFIM sweep plan failed");
     const int nrecv = ctx->log2world;
     const bool p2p = nrecv > 0 && ctx->p2p_ok && ctx->arena_stride >= (int64_t)op->n_loc;
+    const bool prepushed = exchange != XCH_PUSH;
     DSEA_ARG(nrecv == 0 || p2p || work != nullptr, "sharded TFIM matvec needs a work buffer");
     DSEA_ARG(!prepushed || p2p, "prepushed input without a peer arena");
+    DSEA_ARG((in_scale == nullptr && q_out == nullptr) ||
+                 (!mode_adj && pipe_eligible(ctx, sw[0], 1ull << (L - sw[0].T))),
+             "fused input scaling needs the pipelined first sweep");
 
     if (p2p) {         // partners' shards arrive in the arena by peer stores
         if (!prepushed) {
+            const int xt = prof_begin(ctx, PK_EXCHANGE, 8.0 * (double)op->n_loc * nrecv, st);
             if (!ctx->fresh_collective) DSEA_TRY(comm_barrier(ctx, st));   // partners finished reading the arena
             DSEA_TRY(push_to_peers(ctx, v, op->n_loc, st));
             DSEA_TRY(comm_barrier(ctx, st));                               // partners' stores have landed
+            prof_end(ctx, xt, st);
         }
     } else if (nrecv > 0) {   // top-bit shards travel on the side stream while the local sweeps run
         DSEA_CUDA(cudaEventRecord(ctx->ev_ready, st));
@@ -417,21 +539,32 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
     }
     const bool want_dot = mode_adj || (dot_out != nullptr);
     int total_partials = 0;
-    const int tok = prof_begin(ctx, mode_adj ? PK_ADJOINT : PK_MATVEC, 16.0 * (double)op->n_loc, st);
+    int tok = prof_begin(ctx, mode_adj ? PK_ADJOINT : PK_MATVEC, 16.0 * (double)op->n_loc, st);
     for (int j = 0; j < ns; ++j) {
         const bool last = (j == ns - 1);
+        if (last && p2p && exchange == XCH_PREPUSHED_BARRIER) {
+            // the local sweeps above overlapped the partners' stores; wait for them only now
+            prof_end(ctx, tok, st);
+            const int xt = prof_begin(ctx, PK_EXCHANGE, 0.0, st);
+            DSEA_TRY(comm_barrier(ctx, st));
+            prof_end(ctx, xt, st);
+            tok = prof_begin(ctx, mode_adj ? PK_ADJOINT : PK_MATVEC, 0.0, st);
+        }
         SweepParams p;
         p.v = v;
         p.uin = u;
         p.uout = u;
         p.g = g;
         p.shift = shift;
+        p.in_scale = (j == 0) ? in_scale : nullptr;
+        p.q_out = (j == 0) ? q_out : nullptr;
         p.recv = p2p ? ctx->arena : work;
         p.recv_stride = p2p ? (uint64_t)ctx->arena_stride : (uint64_t)op->n_loc;
         p.remote_scale = (p2p && prepushed) ? remote_scale : nullptr;
         p.guard = ctx->guard;
         p.no_diag = (!mode_adj && g == nullptr) ? 1 : 0;
         p.use_tma = (ctx->tfim_tma && sw[j].c == sw[j].T && (((uintptr_t)v) & 127u) == 0) ? 1 : 0;
+        p.l2_prefetch = ctx->tfim_l2_prefetch;
         p.nrecv = last ? nrecv : 0;
         p.rank_off = (uint64_t)ctx->rank << L;
         p.n_loc = (uint64_t)op->n_loc;
@@ -440,13 +573,13 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.c = sw[j].c;
         p.hshift = sw[j].hshift;
         p.b0 = sw[j].b0;
+        p.ndirect = sw[j].ndirect;
+        p.upbits = L - (sw[j].hshift + sw[j].T - sw[j].c);
+        p.fast_up = sw[j].ndirect > 0 ? 1 : 0;
         p.ntiles = 1ull << (L - sw[j].T);
         // full 2^13 tiles take the persistent double-buffered kernel (one CTA per SM)
-        // (the adjoint reduction keeps the 2-CTA/SM generic kernel: it has no output stream to overlap)
-        // and so does a sweep that adds remote shards: its extra HBM reads sit in the epilogue, where the
-        // 2-CTA/SM kernel hides their latency better — measured 81.7 vs 99.3 ms per solve at P=2)
-        const bool pipe = ctx->tfim_pipeline && !mode_adj && p.nrecv == 0 && p.T == kPipeT && (p.b0 == 0 || p.c <= 10) &&
-                          p.ntiles >= 2;
+        const bool pipe = pipe_eligible(ctx, sw[j], p.ntiles) && !(mode_adj && !ctx->tfim_pipe_adjoint) &&
+                          !(p.nrecv > 0 && !ctx->tfim_pipe_remote);
         int grid = pipe ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
                         : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
@@ -472,19 +605,22 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
 }
 
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
-               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st, bool prepushed,
-               const double* remote_scale) {
-    return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st, prepushed, remote_scale);
+               double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st, int exchange,
+               const double* remote_scale, const double* in_scale, double* q_out) {
+    // with a fused input scale the dot partner is the SCALED input, which the kernel holds in registers (w == v)
+    return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st, exchange, remote_scale,
+                    in_scale, q_out);
 }
 
 // u = (dH/dg) v: the same sweeps with g = 1 and the diagonal dropped (g == nullptr selects this).
 int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st) {
-    return tfim_run(ctx, op, false, nullptr, nullptr, v, u, v, nullptr, work, st);
+    return tfim_run(ctx, op, false, nullptr, nullptr, v, u, v, nullptr, work, st, XCH_PUSH, nullptr, nullptr, nullptr);
 }
 
 int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
                  double* work, cudaStream_t st) {
-    return tfim_run(ctx, op, true, nullptr, nullptr, v2, nullptr, v1, out, work, st);
+    return tfim_run(ctx, op, true, nullptr, nullptr, v2, nullptr, v1, out, work, st, XCH_PUSH, nullptr, nullptr,
+                    nullptr);
 }
 
 }  // namespace dsea
@@ -502,17 +638,17 @@ extern "C" double dsea_tfim_diag(int N, int64_t s) {
 }
 
 // Host-callable view of the sweep schedule (for the CPU tests of the index logic): writes up to 40 rows
-// {T, c, hshift, b0} and returns the number of sweeps (negative on failure).
-extern "C" int dsea_tfim_plan(int local_bits, int tile_bits, int run_bits, int* out4x40) {
+// {T, c, hshift, b0, ndirect} and returns the number of sweeps (negative on failure).  `allow_direct` selects the
+// production plan (direct loads for up to 5 top bits) or the pure shared-memory plan.
+extern "C" int dsea_tfim_plan(int local_bits, int tile_bits, int run_bits, int allow_direct, int* out5x40) {
     dsea::Sweep sw[dsea::kMaxSweeps];
-    if (tile_bits > 14) tile_bits = 14;
-    if (tile_bits < 3) tile_bits = 3;
-    const int n = dsea::plan_sweeps(local_bits, tile_bits, run_bits, sw);
+    const int n = dsea::plan_sweeps(local_bits, dsea::clamp_tile_bits(tile_bits), run_bits, allow_direct != 0, sw);
     for (int j = 0; j < n && j < dsea::kMaxSweeps; ++j) {
-        out4x40[4 * j + 0] = sw[j].T;
-        out4x40[4 * j + 1] = sw[j].c;
-        out4x40[4 * j + 2] = sw[j].hshift;
-        out4x40[4 * j + 3] = sw[j].b0;
+        out5x40[5 * j + 0] = sw[j].T;
+        out5x40[5 * j + 1] = sw[j].c;
+        out5x40[5 * j + 2] = sw[j].hshift;
+        out5x40[5 * j + 3] = sw[j].b0;
+        out5x40[5 * j + 4] = sw[j].ndirect;
     }
     return n;
 }
