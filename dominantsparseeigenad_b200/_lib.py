@@ -39,7 +39,7 @@ PROTOTYPES = {
     "dsea_col_stride": (C.c_int64, [C.c_int64]),
     "dsea_tfim_flip_index": (C.c_int64, [C.c_int, C.c_int64, C.c_int]),
     "dsea_tfim_diag": (C.c_double, [C.c_int, C.c_int64]),
-    "dsea_tfim_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "dsea_tfim_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "dsea_matvec": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                               c_double_p, c_stream]),
     "dsea_tfim_dHdg": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_stream]),

@@ -81,12 +81,13 @@ size_t prof_mark(const dsea_ctx* ctx) { return ctx->prof ? ctx->prof->used : 0; 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
-                    double* u, double* dot_out, double* work, cudaStream_t st, bool prepushed = false,
-                    const double* remote_scale = nullptr) {
+                    double* u, double* dot_out, double* work, cudaStream_t st, int exchange = XCH_PUSH,
+                    const double* remote_scale = nullptr, const double* in_scale = nullptr, double* q_out = nullptr) {
     switch (op->kind) {
         case DSEA_OP_TFIM:
             DSEA_ARG(param != nullptr, "TFIM operator needs the device scalar g");
-            return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st, prepushed, remote_scale);
+            return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st, exchange, remote_scale, in_scale,
+                              q_out);
         case DSEA_OP_CSR:
             return csr_apply(ctx, op, param, shift, v, u, dot_out, st);
         case DSEA_OP_DENSE:
@@ -139,8 +140,10 @@ static int lanczos_start_impl(dsea_ctx* ctx, int64_t n, double* Q, cudaStream_t 
 // `alpha_ready`: scal[S_ALPHA_L] already holds q_i . u (epilogue of the matvec); otherwise it is computed here.
 // `push_next`: pass 2 also stores the new (un-normalised) vector into the partners' arenas, so the next
 // matvec finds its remote shards already in place (the beta^2 reduction that follows is the barrier).
+// `normalise`: scale the new column by 1 / beta here (K3); false when the next matvec's first sweep does it (fused).
 static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i, double* Q, const double* u,
-                             double* alpha, double* beta, cudaStream_t st, bool alpha_ready, bool push_next = false) {
+                             double* alpha, double* beta, cudaStream_t st, bool alpha_ready, bool push_next = false,
+                             bool normalise = true) {
     const int m = i + 1;
     const double* qi = Q + (int64_t)i * ldq;
     if (!alpha_ready) DSEA_TRY(dot(ctx, n, qi, u, ctx->scal + S_ALPHA_L, st));
@@ -161,7 +164,7 @@ static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i
     lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, alpha, beta, i, more ? 1 : 0);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    if (more) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));        // :70,75
+    if (more && normalise) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));   // :70,75
     return DSEA_OK;
 }
 
@@ -308,6 +311,13 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);
+    else if (!strcmp(key, "tfim_pipe_threads")) ctx->tfim_pipe_threads = (value == 256) ? 256 : 512;
+    else if (!strcmp(key, "tfim_direct")) ctx->tfim_direct = (value != 0);
+    else if (!strcmp(key, "tfim_fuse_scale")) ctx->tfim_fuse_scale = (value != 0);
+    else if (!strcmp(key, "tfim_l2_prefetch")) ctx->tfim_l2_prefetch = (value != 0);
+    else if (!strcmp(key, "tfim_pipe_adjoint")) ctx->tfim_pipe_adjoint = (value != 0);
+    else if (!strcmp(key, "tfim_pipe_remote")) ctx->tfim_pipe_remote = (value != 0);
+    else if (!strcmp(key, "cg_fuse_push")) ctx->cg_fuse_push = (value != 0);
     else if (!strcmp(key, "mailbox")) { if (value == 0) ctx->mail_ok = false; }
     else {
         set_error("unknown option %s", key);
@@ -428,11 +438,17 @@ int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, i
     double* opwork = work + ldq;
     DSEA_TRY(lanczos_start_impl(ctx, n, Q, st));
     const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->p2p_ok && ctx->arena_stride >= n;
+    // K3 fused into K1: pass 2 leaves the un-normalised r in column i+1; the first sweep of the next matvec reads it,
+    // multiplies by 1 / beta (device scalar), writes q back in place and produces u from it (Lanczos.py:70-71).
+    const bool fuse_scale = op->kind == DSEA_OP_TFIM && tfim_can_fuse_scale(ctx, op);
     for (int i = 0; i < k; ++i) {
         const bool pre = fuse_push && i > 0;
-        DSEA_TRY(apply_op(ctx, op, param, nullptr, Q + (int64_t)i * ldq, u, ctx->scal + S_ALPHA_L, opwork, st, pre,
-                          ctx->scal + S_INVBETA));                                  // Lanczos.py:54-55,71-72 (alpha in the epilogue)
-        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, true, fuse_push));
+        double* qi = Q + (int64_t)i * ldq;
+        const bool fs = fuse_scale && i > 0;
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, qi, u, ctx->scal + S_ALPHA_L, opwork, st,
+                          pre ? XCH_PREPUSHED : XCH_PUSH, ctx->scal + S_INVBETA, fs ? ctx->scal + S_INVBETA : nullptr,
+                          fs ? qi : nullptr));                                     // Lanczos.py:54-55,71-72 (alpha in the epilogue)
+        DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, true, fuse_push, !fuse_scale));
     }
     return lanczos_ritz_impl(ctx, n, ldq, k, which, Q, alpha, beta, evals, evec_min, evec_max, info_host, st);
 }
@@ -522,7 +538,12 @@ int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double*
     if (maxit <= 0) maxit = n;                                                         // CG.py:32
     DSEA_TRY(cg_setup(ctx, eps, maxit, st));
     DSEA_TRY(apply_op(ctx, op, param, shift, x, Ad, nullptr, opwork, st));             // CG.py:27
-    DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st));
+    // sharded TFIM: the kernels that write the search direction d also store it into the partners' arenas, so the
+    // matvec of d needs no push pass; a single barrier before its last sweep orders the stores (cg_fuse_push)
+    const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->cg_fuse_push && ctx->p2p_ok && ctx->arena_stride >= n;
+    PeerPtrs pp = peer_ptrs(ctx);
+    if (fuse_push && !ctx->fresh_collective) DSEA_TRY(comm_barrier(ctx, st));          // partners are done reading x's shards
+    DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st, fuse_push ? &pp : nullptr));
     ctx->guard = ctx->scal + S_DONE;
     const size_t prof_first = prof_mark(ctx);
     int status = DSEA_OK;
@@ -534,8 +555,9 @@ int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double*
         const int64_t chunk = ctx->cg_check_every;
         for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
             prof_guard_key(ctx, 2 * (issued + q));
-            status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st);   // one matvec / iteration
-            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st);
+            status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st,
+                              fuse_push ? XCH_PREPUSHED_BARRIER : XCH_PUSH);                   // one matvec / iteration
+            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st, fuse_push ? &pp : nullptr);
         }
         if (status != DSEA_OK) break;
         issued += chunk;

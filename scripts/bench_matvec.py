@@ -1,13 +1,23 @@
 """Micro-benchmark of the TFIM operator kernels (K1 / K6) on one GPU.
 
-    python scripts/bench_matvec.py [--spins 24 26] [--reps 20]
+    python scripts/bench_matvec.py [--spins 24 26] [--reps 20] [--out file.json]
 
-For every size it times dsea_matvec (with and without the dot epilogue + shift) and dsea_adjoint with
-CUDA events, for the generic sweep kernel and for the persistent double-buffered one, checks that the two
-agree, and prints achieved GB/s of the ALGORITHMIC 16 n bytes next to the structural bounds of the
-two-sweep scheme (40 n bytes of HBM traffic; 8 N n bytes through the shared-memory crossbar).
+For every size it times dsea_matvec (plain, and with the shift + dot epilogue the CG loop uses) and
+dsea_adjoint with CUDA events under each kernel variant, checks that all variants agree with the first one,
+and prints achieved GB/s of the ALGORITHMIC 16 n bytes next to the HBM bytes the sweep plan actually moves
+(16 n first sweep + 24 n per further sweep).
+
+Variants (dsea_ctx_set_option knobs):
+  r1_plan      round 1's plan: 32-byte runs (run_bits = 2), no direct bits, 512 threads
+  sweeps3      128-byte runs, no direct bits (a third sweep for the top bits)
+  direct       128-byte runs, top local bits by direct (L2-served) loads                  <- default build
+  direct_nopf  ... without the prefetch.global.L2 hints
+  direct_256   ... with 256 threads x 16 pairs (5 register-resident tile bits)
+  direct_notma ... contiguous tiles staged with LDGSTS instead of TMA bulk copies
+  generic      the non-pipelined 2-CTA/SM kernel with the default plan
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -19,6 +29,18 @@ sys.path.insert(0, ROOT)
 import dominantsparseeigenad_b200 as dsea  # noqa: E402
 from dominantsparseeigenad_b200 import _lib  # noqa: E402
 from dominantsparseeigenad_b200.runtime import ptr, stream_ptr  # noqa: E402
+
+DEFAULTS = {"tfim_pipeline": 1, "tfim_tma": 1, "tfim_run_bits": 0, "tfim_direct": 1, "tfim_pipe_threads": 512,
+            "tfim_l2_prefetch": 1, "tfim_pipe_adjoint": 1}
+VARIANTS = {
+    "r1_plan": {"tfim_run_bits": 2, "tfim_direct": 0},
+    "sweeps3": {"tfim_direct": 0},
+    "direct": {},
+    "direct_nopf": {"tfim_l2_prefetch": 0},
+    "direct_256": {"tfim_pipe_threads": 256},
+    "direct_notma": {"tfim_tma": 0},
+    "generic": {"tfim_pipeline": 0},
+}
 
 
 def time_ms(fn, reps):
@@ -38,9 +60,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spins", type=int, nargs="+", default=[24])
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--variants", nargs="+", default=list(VARIANTS))
+    ap.add_argument("--out", default="")
     args = ap.parse_args()
     rt = dsea.runtime.context()
     lib = rt.lib
+    peak = 6540.2
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = float(json.load(open(pk))["hbm_gbs"])
     out = []
     for N in args.spins:
         m = dsea.TFIM(N)
@@ -51,36 +79,44 @@ def main():
         w = torch.randn(n, dtype=torch.float64, device="cuda")
         u = torch.empty_like(v)
         dot = torch.empty(1, dtype=torch.float64, device="cuda")
-        res = {}
+        adj = torch.empty(1, dtype=torch.float64, device="cuda")
         ref = None
-        for pipe, tma in ((0, 0), (1, 0), (1, 1)):
-            rt.set_option("tfim_pipeline", pipe)
-            rt.set_option("tfim_tma", tma)
+        for name in args.variants:
+            for key, val in {**DEFAULTS, **VARIANTS[name]}.items():
+                rt.set_option(key, val)
+            buf = (C.c_int * 200)()
+            ns = lib.dsea_tfim_plan(N, 13, {**DEFAULTS, **VARIANTS[name]}["tfim_run_bits"],
+                                    {**DEFAULTS, **VARIANTS[name]}["tfim_direct"], buf)
+            plan = [tuple(buf[5 * j:5 * j + 5]) for j in range(ns)]
             st = stream_ptr()
             plain = lambda: _lib.check(lib.dsea_matvec(rt.handle, m.handle, ptr(g), None, ptr(v), ptr(u), None, None, st))
-            cgmv = lambda: _lib.check(lib.dsea_matvec(rt.handle, m.handle, ptr(g), ptr(sh), ptr(v), ptr(u), dot.data_ptr(), None, st))
-            adj = lambda: _lib.check(lib.dsea_adjoint(rt.handle, m.handle, ptr(w), ptr(v), dot.data_ptr(), None, st))
-            t_plain, t_cg, t_adj = time_ms(plain, args.reps), time_ms(cgmv, args.reps), time_ms(adj, args.reps)
+            cgmv = lambda: _lib.check(lib.dsea_matvec(rt.handle, m.handle, ptr(g), ptr(sh), ptr(v), ptr(u), ptr(dot), None, st))
+            adjf = lambda: _lib.check(lib.dsea_adjoint(rt.handle, m.handle, ptr(w), ptr(v), ptr(adj), None, st))
             plain()
             torch.cuda.synchronize()
+            got = u.clone()
+            adjf()
+            a_val = adj.item()
             if ref is None:
-                ref = u.clone()
-                err = 0.0
-            else:
-                err = (u - ref).abs().max().item() / ref.abs().max().item()
-            adj()
-            adjval = dot.item()
-            res[f"pipeline{pipe}_tma{tma}"] = {"matvec_ms": t_plain, "matvec_GBps_of_16n": 16 * n / t_plain / 1e6,
-                                      "matvec_cg_ms": t_cg, "adjoint_ms": t_adj,
-                                      "adjoint_GBps_of_16n": 16 * n / t_adj / 1e6, "rel_diff_vs_generic": err,
-                                      "adjoint_value": adjval}
-        rt.set_option("tfim_pipeline", 1)
-        rt.set_option("tfim_tma", 0)
-        res["bounds_ms_at_6540GBps"] = {"algorithmic_16n": 16 * n / 6540e6, "two_sweep_hbm_40n": 40 * n / 6540e6}
-        out.append({"spins": N, **res})
-        del m, v, w, u, ref
+                ref = (got, a_val)
+            err = (got - ref[0]).abs().max().item() / ref[0].abs().max().item()
+            aerr = abs(a_val - ref[1]) / abs(ref[1])
+            assert err < 1e-13 and aerr < 1e-11, (name, err, aerr)
+            t_plain, t_cg, t_adj = time_ms(plain, args.reps), time_ms(cgmv, args.reps), time_ms(adjf, args.reps)
+            hbm_bytes = (16 + 24 * (ns - 1)) * n
+            row = {"N": N, "variant": name, "plan": plan, "matvec_ms": t_plain, "matvec_shift_dot_ms": t_cg,
+                   "adjoint_ms": t_adj, "algorithmic_GBs": 16 * n / t_plain / 1e6,
+                   "frac_of_16n_roofline": 16 * n / t_plain / 1e6 / peak,
+                   "plan_hbm_bytes_per_el": hbm_bytes / n, "frac_of_plan_traffic": hbm_bytes / t_plain / 1e6 / peak,
+                   "max_rel_diff_vs_first_variant": err}
+            out.append(row)
+            print(json.dumps(row), flush=True)
+        for key, val in DEFAULTS.items():
+            rt.set_option(key, val)
+        del m, v, w, u
         torch.cuda.empty_cache()
-    print(json.dumps(out, indent=1))
+    if args.out:
+        json.dump(out, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":

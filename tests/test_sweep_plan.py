@@ -20,48 +20,73 @@ def lib():
     return _lib.load()
 
 
-def plan(lib, L, T, run=0):
-    buf = (C.c_int * 160)()
-    n = lib.dsea_tfim_plan(L, T, run, buf)
+def plan(lib, L, T, run=0, direct=1):
+    buf = (C.c_int * 200)()
+    n = lib.dsea_tfim_plan(L, T, run, direct, buf)
     assert n > 0, (L, T, run)
-    return [tuple(buf[4 * j:4 * j + 4]) for j in range(n)]
+    return [tuple(buf[5 * j:5 * j + 5]) for j in range(n)]
 
 
 def tile_to_global(L, sw):
-    """Global indices of every (tile, element) of one sweep, as an array [ntiles, 2^T]."""
-    T, c, hshift, b0 = sw
+    """Global indices of every (tile, element) of one sweep, as an array [ntiles, 2^T].  Mirrors tile_base() in
+    tfim.cu: a sweep with direct bits orders its tiles with the UPPER address bits fastest."""
+    T, c, hshift, b0, nd = sw
     ntiles = 1 << (L - T)
     t = np.arange(ntiles, dtype=np.int64)[:, None]
     e = np.arange(1 << T, dtype=np.int64)[None, :]
     mid = hshift - c
-    base = ((t & ((1 << mid) - 1)) << c) | ((t >> mid) << (hshift + T - c))
+    up = L - (hshift + T - c)
+    if nd > 0:
+        assert nd == up
+        t_up, t_mid = t & ((1 << up) - 1), t >> up
+    else:
+        t_mid, t_up = t & ((1 << mid) - 1), t >> mid
+    base = (t_mid << c) | (t_up << (hshift + T - c))
     return base | (e & ((1 << c) - 1)) | ((e >> c) << hshift)
 
 
 @pytest.mark.parametrize("T", [3, 5, 8, 12, 13, 14])
 def test_every_bit_handled_once_and_tiles_are_bijective(lib, T):
     for L in range(1, 31):
-        for run in (0, 2, 4):
-            sweeps = plan(lib, L, T, run)
+        for run, direct in ((0, 1), (0, 0), (2, 1), (4, 0)):
+            sweeps = plan(lib, L, T, run, direct)
             handled = []
-            for (Ts, c, hshift, b0) in sweeps:
+            for (Ts, c, hshift, b0, nd) in sweeps:
                 assert 1 <= Ts <= max(T, 1) or L < T
                 assert 0 < c <= Ts and b0 in (0, c)
+                assert 0 <= nd <= 5 and (nd == 0 or (direct and run == 0))
                 for b in range(b0, Ts):
                     handled.append(b if b < c else hshift + (b - c))
+                handled += [hshift + (Ts - c) + d for d in range(nd)]          # direct bits sit right above the tile
             assert sorted(handled) == list(range(L)), (L, T, run, sweeps)
+            if run == 0 and T >= 10:
+                assert all(c >= 4 for (Ts, c, _, _, _) in sweeps if Ts == T), (L, T, sweeps)   # >= 128-byte runs
             if L <= 16:
                 for sw in sweeps:
                     g = tile_to_global(L, sw)
                     assert np.array_equal(np.sort(g.ravel()), np.arange(1 << L)), (L, T, run, sw)
-                    Ts, c, hshift, b0 = sw
+                    Ts, c, hshift, b0, nd = sw
                     e = np.arange(1 << Ts)
                     for b in range(b0, Ts):
                         spin_bit = b if b < c else hshift + (b - c)
                         assert np.array_equal(g[:, e ^ (1 << b)], g ^ (1 << spin_bit))
 
 
-@pytest.mark.parametrize("N,T,run", [(10, 13, 0), (12, 5, 0), (14, 6, 2), (15, 7, 3)])
+def test_production_plans():
+    """The plans the benchmark sizes get with 13-bit tiles: two sweeps up to 27 local bits (the last one with
+    128-byte runs and <= 5 direct bits), three sweeps beyond; partner tiles of the direct bits are adjacent."""
+    lib = _lib.load()
+    assert plan(lib, 20, 13) == [(13, 13, 13, 0, 0), (13, 6, 13, 6, 0)]
+    assert plan(lib, 22, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 0)]
+    assert plan(lib, 24, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 2)]
+    assert plan(lib, 27, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 5)]
+    assert [s[4] for s in plan(lib, 28, 13)] == [0, 0, 0] and len(plan(lib, 24, 13, direct=0)) == 3
+    assert plan(lib, 23, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 1)]
+    g = tile_to_global(23, (13, 4, 13, 4, 1))[:, 0]            # element 0 of consecutive tiles
+    assert g[1] == g[0] ^ (1 << 22) and g[2] == g[0] ^ (1 << 4)
+
+
+@pytest.mark.parametrize("N,T,run", [(10, 13, 0), (12, 5, 0), (14, 6, 2), (15, 7, 3), (16, 10, 0), (17, 11, 0)])
 def test_emulated_sweeps_reproduce_oracle_matvec(lib, N, T, run):
     from oracle import dsea_oracle as orc
     g = 1.3
@@ -69,13 +94,15 @@ def test_emulated_sweeps_reproduce_oracle_matvec(lib, N, T, run):
     v = rng.standard_normal(1 << N)
     u = None
     for j, sw in enumerate(plan(lib, N, T, run)):
-        Ts, c, hshift, b0 = sw
+        Ts, c, hshift, b0, nd = sw
         gi = tile_to_global(N, sw)
         tile = v[gi]
         e = np.arange(1 << Ts)
         acc = np.zeros_like(tile)
         for b in range(b0, Ts):
             acc += tile[:, e ^ (1 << b)]
+        for d in range(nd):                                    # direct bits: partner elements straight from the vector
+            acc += v[gi ^ (1 << (hshift + Ts - c + d))]
         if j == 0:
             diag = np.array([lib.dsea_tfim_diag(N, int(s)) for s in range(1 << N)])
             u = np.empty_like(v)
