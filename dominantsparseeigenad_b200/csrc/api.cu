@@ -311,7 +311,9 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);
-    else if (!strcmp(key, "tfim_pipe_threads")) ctx->tfim_pipe_threads = (value == 256) ? 256 : 512;
+    else if (!strcmp(key, "tfim_pipe_threads")) ctx->tfim_pipe_threads = (value == 256 || value == 1024) ? (int)value : 512;
+    else if (!strcmp(key, "tfim_unroll")) ctx->tfim_unroll = (value != 0);
+    else if (!strcmp(key, "tfim_generic_min_operands")) ctx->tfim_generic_min_operands = (int)value;
     else if (!strcmp(key, "tfim_direct")) ctx->tfim_direct = (value != 0);
     else if (!strcmp(key, "tfim_fuse_scale")) ctx->tfim_fuse_scale = (value != 0);
     else if (!strcmp(key, "tfim_l2_prefetch")) ctx->tfim_l2_prefetch = (value != 0);

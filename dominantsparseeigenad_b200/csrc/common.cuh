@@ -132,10 +132,12 @@ struct dsea_ctx {
     int tfim_run_bits = 0;              // 0 = auto
     int tfim_pipeline = 1;              // persistent double-buffered sweep kernel for full 2^13 tiles
     int tfim_tma = 1;                   // stage contiguous tiles with TMA bulk copies (UBLKCP + mbarrier) instead of LDGSTS
-    int tfim_pipe_threads = 512;        // 512: 8 pairs / thread (4 register bits); 256: 16 pairs / thread (5 register bits)
+    int tfim_pipe_threads = 512;        // 256 / 512 / 1024 threads: 16 / 8 / 4 pairs per thread (5 / 4 / 3 register-resident tile bits)
+    int tfim_generic_min_operands = 4;  // last sweep: direct bits + remote bits from which the generic kernel is used
+    int tfim_unroll = 1;                // compile-time flip-bit range in the pipelined kernel (fully unrolled LDS loop)
     int tfim_direct = 1;                // top local bits beyond two sweeps by direct (L2-served) loads instead of a third sweep
     int tfim_fuse_scale = 1;            // fold the Lanczos normalisation q = r / beta into the first matvec sweep
-    int tfim_l2_prefetch = 1;           // prefetch.global.L2 the next tile's epilogue operands
+    int tfim_l2_prefetch = 0;           // prefetch.global.L2 the next tile's epilogue operands
     int tfim_pipe_adjoint = 1;          // adjoint contraction (K6) through the pipelined kernel
     int tfim_pipe_remote = 1;           // last sweep of a sharded matvec through the pipelined kernel
     int cg_fuse_push = 1;               // CG direction update stores d into the partners' arenas

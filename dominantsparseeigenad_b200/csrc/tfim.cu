@@ -31,7 +31,7 @@
 
 namespace dsea {
 
-constexpr int kMaxDirect = 5;
+constexpr int kMaxDirect = 4;   // measured: from 5 direct bits on, a third sweep is faster (L = 27: 1.70 vs 1.76 ms)
 
 struct Sweep {
     int T;        // tile bits
@@ -221,18 +221,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                  : "memory");
 }
 
-template <int MODE, int THREADS>
+// LB: compile-time first shared-memory flip bit (1: contiguous first sweep; 4: strided sweep with 128-byte runs;
+// 0: taken from the plan at run time).  With LB known the flip loop is fully unrolled, so the LDS of the next bit
+// are in flight while the adds of the current one retire.
+template <int MODE, int THREADS, int LB>
 __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
     constexpr int T = kPipeT;
-    constexpr int PAIRS = (1 << (T - 1)) / THREADS;            // 8 (512 threads) or 16 (256 threads)
-    constexpr int RBITS = (PAIRS == 8) ? 3 : 4;                // register-resident top tile bits
-    constexpr int RB0 = T - RBITS;                             // first of them: tile bit 10 or 9
+    constexpr int PAIRS = (1 << (T - 1)) / THREADS;            // 16 / 8 / 4 pairs per thread (256 / 512 / 1024 threads)
+    constexpr int RBITS = (PAIRS == 16) ? 4 : (PAIRS == 8 ? 3 : 2);   // register-resident top tile bits
+    constexpr int RB0 = T - RBITS;                             // first of them
     extern __shared__ __align__(128) double bufs[];            // 2 x 2^13 doubles
     __shared__ double red[32];
     __shared__ __align__(8) uint64_t mbar[2];
     if (p.guard && *p.guard != 0.0) return;
     const bool tma = p.use_tma != 0;                           // contiguous tiles only (first sweep)
-    uint32_t phase[2] = {0u, 0u};
+    uint32_t phase0 = 0u, phase1 = 0u;
     if (tma) {
         if (threadIdx.x == 0) {
             mbar_init(&mbar[0], 1);
@@ -249,13 +252,10 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
     const double shift = (MODE == MODE_FIRST && p.shift) ? *p.shift : 0.0;
     const double scl = (MODE == MODE_FIRST && p.in_scale) ? *p.in_scale : 1.0;
     const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
-    const int bstart = p.b0 > 1 ? p.b0 : 1;
+    const int bstart = LB > 0 ? LB : (p.b0 > 1 ? p.b0 : 1);
     double part = 0.0;
 
-    uint32_t e[PAIRS];                                         // tile offsets of this thread's pairs
-#pragma unroll
-    for (int j = 0; j < PAIRS; ++j) e[j] = 2u * (threadIdx.x + THREADS * j);
-
+    auto eoff = [&](int j) -> uint32_t { return 2u * (threadIdx.x + THREADS * j); };   // tile offset of pair j
     auto gidx = [&](uint64_t base, uint32_t ee) -> uint64_t {
         return base | (ee & cmask) | ((uint64_t)(ee >> c) << p.hshift);
     };
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < PAIRS; ++j) cp_async16(buf + e[j], p.v + gidx(base, e[j]));
+            for (int j = 0; j < PAIRS; ++j) cp_async16(buf + eoff(j), p.v + gidx(base, eoff(j)));
             cp_async_commit();
         }
         if (p.l2_prefetch && c >= 4) {                          // the next tile's epilogue operands, one 128 B line each
@@ -294,43 +294,58 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
         const uint64_t base = tile_base(p, t);
         if (tn < p.ntiles) prefetch(tn, bufs + ((size_t)(stage ^ 1) << T), stage ^ 1);
         if (tma) {
-            mbar_wait(&mbar[stage], phase[stage]);                // the bulk copy's bytes have landed
-            phase[stage] ^= 1u;
+            if (stage == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }    // the bulk copy's bytes have landed
+            else { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
         } else {
             if (tn < p.ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncthreads();
         }
 
-        double2 x[PAIRS], a[PAIRS];
+        double2 a[PAIRS];
+        {
+            double2 x[PAIRS];
 #pragma unroll
-        for (int j = 0; j < PAIRS; ++j) x[j] = *reinterpret_cast<const double2*>(buf + e[j]);
+            for (int j = 0; j < PAIRS; ++j) x[j] = *reinterpret_cast<const double2*>(buf + eoff(j));
 #pragma unroll
-        for (int j = 0; j < PAIRS; ++j)                           // tile bit 0: the pair partner
-            a[j] = (p.b0 == 0) ? make_double2(x[j].y, x[j].x) : make_double2(0.0, 0.0);
+            for (int j = 0; j < PAIRS; ++j)                       // tile bit 0: the pair partner
+                a[j] = (p.b0 == 0) ? make_double2(x[j].y, x[j].x) : make_double2(0.0, 0.0);
 #pragma unroll
-        for (int jb = 0; jb < RBITS; ++jb) {                      // register-resident flips: tile bits RB0 .. 12
-            if (RB0 + jb >= p.b0) {
+            for (int jb = 0; jb < RBITS; ++jb) {                  // register-resident flips: tile bits RB0 .. 12
+                if (LB > 0 || RB0 + jb >= p.b0) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) {
+                        a[j].x += x[j ^ (1 << jb)].x;
+                        a[j].y += x[j ^ (1 << jb)].y;
+                    }
+                }
+            }
+        }                                                         // x is dead here: re-read from the tile when needed
+        if (LB > 0) {
+#pragma unroll
+            for (int b = LB; b < RB0; ++b) {                      // the other tile bits from shared memory
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
-                    a[j].x += x[j ^ (1 << jb)].x;
-                    a[j].y += x[j ^ (1 << jb)].y;
+                    const double2 y = *reinterpret_cast<const double2*>(buf + (eoff(j) ^ (1u << b)));
+                    a[j].x += y.x;
+                    a[j].y += y.y;
+                }
+            }
+        } else {
+            for (int b = bstart; b < RB0; ++b) {
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    const double2 y = *reinterpret_cast<const double2*>(buf + (eoff(j) ^ (1u << b)));
+                    a[j].x += y.x;
+                    a[j].y += y.y;
                 }
             }
         }
-        for (int b = bstart; b < RB0; ++b) {                      // the other tile bits from shared memory
-#pragma unroll
-            for (int j = 0; j < PAIRS; ++j) {
-                const double2 y = *reinterpret_cast<const double2*>(buf + (e[j] ^ (1u << b)));
-                a[j].x += y.x;
-                a[j].y += y.y;
-            }
-        }
-        // ---- epilogue: operands that live in global memory (L2-resident when prefetched) ----
+        // ---- epilogue: operands that live in global memory (L2-resident partner tiles, u, w, arena slots) ----
         for (int d = 0; d < p.ndirect; ++d) {                     // top local bits: partner tiles
             const uint64_t dbit = 1ull << (dpos + d);
             double2 y[PAIRS];
 #pragma unroll
-            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(p.v + (gidx(base, e[j]) ^ dbit));
+            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(p.v + (gidx(base, eoff(j)) ^ dbit));
 #pragma unroll
             for (int j = 0; j < PAIRS; ++j) {
                 a[j].x += y[j].x;
@@ -341,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
             const double* slot = p.recv + (uint64_t)q * p.recv_stride;
             double2 y[PAIRS];
 #pragma unroll
-            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(slot + gidx(base, e[j]));
+            for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(slot + gidx(base, eoff(j)));
 #pragma unroll
             for (int j = 0; j < PAIRS; ++j) {
                 a[j].x += rscale * y[j].x;
@@ -351,49 +366,52 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
         if (MODE == MODE_ADJ) {
             double2 wv[PAIRS];
 #pragma unroll
-            for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, e[j]));
+            for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, eoff(j)));
 #pragma unroll
             for (int j = 0; j < PAIRS; ++j) part -= wv[j].x * a[j].x + wv[j].y * a[j].y;
         } else {
+            const bool dot_self = p.w != nullptr && p.w == p.v;
             double2 o[PAIRS];
             if (MODE == MODE_FIRST) {
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
-                    const uint64_t s = p.rank_off | gidx(base, e[j]);
+                    double2 x = *reinterpret_cast<const double2*>(buf + eoff(j));
+                    const uint64_t gi = gidx(base, eoff(j));
+                    const uint64_t s = p.rank_off | gi;
                     const double d0 = p.no_diag ? 0.0 : tfim_diag_dev(s, p.N, nmask);
                     const double d1 = p.no_diag ? 0.0 : tfim_diag_dev(s | 1ull, p.N, nmask);
-                    o[j].x = scl * ((d0 - shift) * x[j].x - g * a[j].x);
-                    o[j].y = scl * ((d1 - shift) * x[j].y - g * a[j].y);
-                    x[j].x *= scl;                                // the logical input (for q_out and the dot)
-                    x[j].y *= scl;
-                }
-                if (p.q_out) {
-#pragma unroll
-                    for (int j = 0; j < PAIRS; ++j) stg2(p.q_out + gidx(base, e[j]), x[j]);
+                    o[j].x = scl * ((d0 - shift) * x.x - g * a[j].x);
+                    o[j].y = scl * ((d1 - shift) * x.y - g * a[j].y);
+                    x.x *= scl;                                   // the logical input (for q_out and the dot)
+                    x.y *= scl;
+                    if (p.q_out) stg2(p.q_out + gi, x);
+                    if (dot_self) part += x.x * o[j].x + x.y * o[j].y;
                 }
             } else {
                 double2 ui[PAIRS];
 #pragma unroll
-                for (int j = 0; j < PAIRS; ++j) ui[j] = ldg2(p.uin + gidx(base, e[j]));
+                for (int j = 0; j < PAIRS; ++j) ui[j] = ldg2(p.uin + gidx(base, eoff(j)));
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
                     o[j].x = ui[j].x - g * a[j].x;
                     o[j].y = ui[j].y - g * a[j].y;
                 }
+                if (dot_self) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) {
+                        const double2 x = *reinterpret_cast<const double2*>(buf + eoff(j));
+                        part += x.x * o[j].x + x.y * o[j].y;
+                    }
+                }
             }
 #pragma unroll
-            for (int j = 0; j < PAIRS; ++j) stg2(p.uout + gidx(base, e[j]), o[j]);
-            if (p.w) {
-                if (p.w == p.v) {
+            for (int j = 0; j < PAIRS; ++j) stg2(p.uout + gidx(base, eoff(j)), o[j]);
+            if (p.w && !dot_self) {
+                double2 wv[PAIRS];
 #pragma unroll
-                    for (int j = 0; j < PAIRS; ++j) part += x[j].x * o[j].x + x[j].y * o[j].y;
-                } else {
-                    double2 wv[PAIRS];
+                for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, eoff(j)));
 #pragma unroll
-                    for (int j = 0; j < PAIRS; ++j) wv[j] = ldg2(p.w + gidx(base, e[j]));
-#pragma unroll
-                    for (int j = 0; j < PAIRS; ++j) part += wv[j].x * o[j].x + wv[j].y * o[j].y;
-                }
+                for (int j = 0; j < PAIRS; ++j) part += wv[j].x * o[j].x + wv[j].y * o[j].y;
             }
         }
         __syncthreads();          // everyone is done with `buf` before the next prefetch overwrites it
@@ -452,26 +470,34 @@ static int plan_sweeps(int L, int Tmax, int run_bits, bool allow_direct, Sweep* 
     return rem > 0 ? -1 : n;
 }
 
-template <int MODE, int THREADS>
+template <int MODE, int THREADS, int LB>
 static int launch_pipe(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream_t st) {
     const size_t smem2 = (sizeof(double) << kPipeT) * 2;
     static bool done = false;
     if (!done) {
-        DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_pipe_kernel<MODE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem2));
+        DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_pipe_kernel<MODE, THREADS, LB>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         done = true;
     }
-    tfim_sweep_pipe_kernel<MODE, THREADS><<<grid, THREADS, smem2, st>>>(p);
+    tfim_sweep_pipe_kernel<MODE, THREADS, LB><<<grid, THREADS, smem2, st>>>(p);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
 }
 
+template <int MODE, int THREADS>
+static int launch_pipe_lb(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream_t st) {
+    if (ctx->tfim_unroll && p.b0 == 0) return launch_pipe<MODE, THREADS, 1>(ctx, p, grid, st);
+    if (ctx->tfim_unroll && p.b0 == 4 && p.c == 4) return launch_pipe<MODE, THREADS, 4>(ctx, p, grid, st);
+    return launch_pipe<MODE, THREADS, 0>(ctx, p, grid, st);
+}
+
 template <int MODE>
 static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, bool pipe, cudaStream_t st) {
     if (pipe) {
-        if (ctx->tfim_pipe_threads == 256) return launch_pipe<MODE, 256>(ctx, p, grid, st);
-        return launch_pipe<MODE, 512>(ctx, p, grid, st);
+        if (ctx->tfim_pipe_threads == 256) return launch_pipe_lb<MODE, 256>(ctx, p, grid, st);
+        if (ctx->tfim_pipe_threads == 1024) return launch_pipe_lb<MODE, 1024>(ctx, p, grid, st);
+        return launch_pipe_lb<MODE, 512>(ctx, p, grid, st);
     }
     const size_t smem = sizeof(double) << p.T;
     static bool attr_done[3] = {false, false, false};
@@ -578,8 +604,13 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.fast_up = sw[j].ndirect > 0 ? 1 : 0;
         p.ntiles = 1ull << (L - sw[j].T);
         // full 2^13 tiles take the persistent double-buffered kernel (one CTA per SM)
+        // ... except a last sweep with many global-memory operands per element (direct partner tiles + arena slots): its
+        // epilogue is a chain of dependent load rounds, which the 2-CTA/SM generic kernel hides better (measured at
+        // L = 26, 4 direct bits: 0.77 vs 0.84 ms per matvec; at L = 24 / 25 with 2 / 3 the pipelined kernel wins)
+        // (the adjoint reduction has no output stream and stays pipelined: 0.48 vs 0.63 ms at L = 26)
         const bool pipe = pipe_eligible(ctx, sw[j], p.ntiles) && !(mode_adj && !ctx->tfim_pipe_adjoint) &&
-                          !(p.nrecv > 0 && !ctx->tfim_pipe_remote);
+                          !(p.nrecv > 0 && !ctx->tfim_pipe_remote) &&
+                          !(!mode_adj && p.ndirect + p.nrecv >= ctx->tfim_generic_min_operands);
         int grid = pipe ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
                         : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));

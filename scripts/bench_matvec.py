@@ -11,8 +11,11 @@ Variants (dsea_ctx_set_option knobs):
   r1_plan      round 1's plan: 32-byte runs (run_bits = 2), no direct bits, 512 threads
   sweeps3      128-byte runs, no direct bits (a third sweep for the top bits)
   direct       128-byte runs, top local bits by direct (L2-served) loads                  <- default build
-  direct_nopf  ... without the prefetch.global.L2 hints
-  direct_256   ... with 256 threads x 16 pairs (5 register-resident tile bits)
+  direct_allpipe / direct_lastgeneric  ... last sweep always pipelined / always the generic 2-CTA/SM kernel
+  direct_pf    ... with prefetch.global.L2 hints for the next tile's epilogue operands
+  direct_nounroll ... flip-bit loop bounds taken at run time (no unrolling)
+  direct_256 / direct_1024  ... 256 threads x 16 pairs / 1024 threads x 4 pairs (5 / 3 register-resident tile bits)
+  sweeps3_1024 three sweeps with 1024 threads
   direct_notma ... contiguous tiles staged with LDGSTS instead of TMA bulk copies
   generic      the non-pipelined 2-CTA/SM kernel with the default plan
 """
@@ -31,13 +34,18 @@ from dominantsparseeigenad_b200 import _lib  # noqa: E402
 from dominantsparseeigenad_b200.runtime import ptr, stream_ptr  # noqa: E402
 
 DEFAULTS = {"tfim_pipeline": 1, "tfim_tma": 1, "tfim_run_bits": 0, "tfim_direct": 1, "tfim_pipe_threads": 512,
-            "tfim_l2_prefetch": 1, "tfim_pipe_adjoint": 1}
+            "tfim_l2_prefetch": 0, "tfim_pipe_adjoint": 1, "tfim_unroll": 1, "tfim_generic_min_operands": 4}
 VARIANTS = {
-    "r1_plan": {"tfim_run_bits": 2, "tfim_direct": 0},
+    "r1_plan": {"tfim_run_bits": 2, "tfim_direct": 0, "tfim_unroll": 0},
     "sweeps3": {"tfim_direct": 0},
     "direct": {},
-    "direct_nopf": {"tfim_l2_prefetch": 0},
+    "direct_allpipe": {"tfim_generic_min_operands": 99},
+    "direct_lastgeneric": {"tfim_generic_min_operands": 1},
+    "direct_pf": {"tfim_l2_prefetch": 1},
+    "direct_nounroll": {"tfim_unroll": 0},
     "direct_256": {"tfim_pipe_threads": 256},
+    "direct_1024": {"tfim_pipe_threads": 1024},
+    "sweeps3_1024": {"tfim_direct": 0, "tfim_pipe_threads": 1024},
     "direct_notma": {"tfim_tma": 0},
     "generic": {"tfim_pipeline": 0},
 }

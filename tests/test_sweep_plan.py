@@ -54,7 +54,7 @@ def test_every_bit_handled_once_and_tiles_are_bijective(lib, T):
             for (Ts, c, hshift, b0, nd) in sweeps:
                 assert 1 <= Ts <= max(T, 1) or L < T
                 assert 0 < c <= Ts and b0 in (0, c)
-                assert 0 <= nd <= 5 and (nd == 0 or (direct and run == 0))
+                assert 0 <= nd <= 4 and (nd == 0 or (direct and run == 0))
                 for b in range(b0, Ts):
                     handled.append(b if b < c else hshift + (b - c))
                 handled += [hshift + (Ts - c) + d for d in range(nd)]          # direct bits sit right above the tile
@@ -73,13 +73,14 @@ def test_every_bit_handled_once_and_tiles_are_bijective(lib, T):
 
 
 def test_production_plans():
-    """The plans the benchmark sizes get with 13-bit tiles: two sweeps up to 27 local bits (the last one with
-    128-byte runs and <= 5 direct bits), three sweeps beyond; partner tiles of the direct bits are adjacent."""
+    """The plans the benchmark sizes get with 13-bit tiles: two sweeps up to 26 local bits (the last one with
+    128-byte runs and <= 4 direct bits), three sweeps beyond; partner tiles of the direct bits are adjacent."""
     lib = _lib.load()
     assert plan(lib, 20, 13) == [(13, 13, 13, 0, 0), (13, 6, 13, 6, 0)]
     assert plan(lib, 22, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 0)]
     assert plan(lib, 24, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 2)]
-    assert plan(lib, 27, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 5)]
+    assert plan(lib, 26, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 4)]
+    assert plan(lib, 27, 13) == [(13, 13, 13, 0, 0), (13, 6, 13, 6, 0), (13, 6, 20, 6, 0)]
     assert [s[4] for s in plan(lib, 28, 13)] == [0, 0, 0] and len(plan(lib, 24, 13, direct=0)) == 3
     assert plan(lib, 23, 13) == [(13, 13, 13, 0, 0), (13, 4, 13, 4, 1)]
     g = tile_to_global(23, (13, 4, 13, 4, 1))[:, 0]            # element 0 of consecutive tiles
