@@ -468,6 +468,13 @@ def main():
             line["pairs"] = {"config2": {"workload": workload_name(SAMPLE_N, SAMPLE_K, mode),
                                          "ours_s_per_solve": m2["ms_total"] / 1e3 / 5, "ours_e2e_s_per_solve": m2["e2e_s"],
                                          "gpu_launches_per_solve": m2["launches"] / 5, "analytic_check": check(m2)}}
+        if args.basis == "fp64" and not args.spins:
+            # the same workload with the opt-in fp32 shadow basis (half the reorth traffic, fp64 polish): reported
+            # beside the headline, never as the headline (the reference's precision is fp64 throughout)
+            m32 = measure(N, k, "fp32", 3, 2, with_e2e=False, with_clocks=False)
+            line["fp32_shadow_basis"] = {"config": make_config(N, k, "fp32"), "value": m32["ms_total"] / 1e3 / 3,
+                                         "unit": UNIT, "steps": 3, "warmup": 2, "kernels": kernel_table(m32),
+                                         "analytic_check": check(m32), "cg_iterations_per_solve": m32["cg_iters"]}
         if world > 1:
             from dominantsparseeigenad_b200 import selfcheck
             line["selfcheck"] = selfcheck.run()

@@ -35,6 +35,8 @@ def Lanczos(A, k, device=torch.device("cpu"), *, sparse=False, dim=None):
     """
     op, out_dev = _resolve(A, device, sparse, dim)
     _, _, _, st = op.lanczos(None, int(k), _lib.DSEA_MIN, want_info=False)
+    if st.get("basis") == "fp32":
+        raise RuntimeError("Lanczos() returns the fp64 basis; switch runtime.set_basis_precision('fp64') for it")
     n, ldq = op.n_loc, st["ldq"]
     Qk = st["Q"].view(int(k), ldq)[:, :n].t()
     a, b = st["alpha"], st["beta"][: int(k) - 1]

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "dsea_tfim_dHdg": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_stream]),
     "dsea_adjoint": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, c_double_p, c_double_p, c_double_p, c_stream]),
     "dsea_lanczos_work_doubles": (C.c_int64, [C.c_void_p]),
+    "dsea_lanczos_basis_doubles": (C.c_int64, [C.c_void_p, C.c_int]),
     "dsea_lanczos": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p,
                                c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                                C.POINTER(C.c_int64), c_stream]),

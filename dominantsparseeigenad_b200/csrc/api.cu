@@ -82,12 +82,13 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0
 
 static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
                     double* u, double* dot_out, double* work, cudaStream_t st, int exchange = XCH_PUSH,
-                    const double* remote_scale = nullptr, const double* in_scale = nullptr, double* q_out = nullptr) {
+                    const double* remote_scale = nullptr, const double* in_scale = nullptr, double* q_out = nullptr,
+                    bool round_remote = false) {
     switch (op->kind) {
         case DSEA_OP_TFIM:
             DSEA_ARG(param != nullptr, "TFIM operator needs the device scalar g");
             return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st, exchange, remote_scale, in_scale,
-                              q_out);
+                              q_out, round_remote);
         case DSEA_OP_CSR:
             return csr_apply(ctx, op, param, shift, v, u, dot_out, st);
         case DSEA_OP_DENSE:
@@ -308,6 +309,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "basis_fp32")) ctx->basis_fp32 = (value != 0);
+    else if (!strcmp(key, "polish_eps_1e15")) ctx->polish_eps = 1e-15 * (double)(value < 1 ? 1 : value);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);
@@ -425,8 +427,209 @@ int dsea_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const doubl
     return DSEA_ERR_ARG;
 }
 
+// ---- CG core (used by dsea_cg and by the eigenpair polish) ----------------------------------------------------
+static int cg_poll(dsea_ctx* ctx, int slot, cudaStream_t st) {
+    DSEA_CUDA(cudaMemcpyAsync(ctx->pinned + 8 * slot, ctx->scal + S_DONE, 3 * sizeof(double),
+                              cudaMemcpyDeviceToHost, st));          // {done, iters, rnorm}
+    DSEA_CUDA(cudaEventRecord(ctx->ev_poll[slot], st));
+    return DSEA_OK;
+}
+
+// `proj` (may be NULL): after every operator application the result is projected off `proj` (unit vector), i.e. the
+// system solved is P (A - shift) P x = b with P = 1 - proj proj^T — the Jacobi-Davidson correction equation used by
+// the eigenpair polish.  b and x0 must be orthogonal to proj.
+static int cg_solve_impl(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* b,
+                         double* x, double* work, double eps, int64_t maxit, const double* proj, int64_t* iters_host,
+                         cudaStream_t st) {
+    const int64_t n = op->n_loc, ld = col_stride(n);
+    double* r = work;
+    double* d = work + ld;
+    double* Ad = work + 2 * ld;
+    double* opwork = work + 3 * ld;
+    if (maxit <= 0) maxit = n;                                                         // CG.py:32
+    DSEA_TRY(cg_setup(ctx, eps, maxit, st));
+    DSEA_TRY(apply_op(ctx, op, param, shift, x, Ad, nullptr, opwork, st));             // CG.py:27
+    if (proj) DSEA_TRY(project(ctx, n, proj, Ad, Ad, st));
+    // sharded TFIM: the kernels that write the search direction d also store it into the partners' arenas, so the
+    // matvec of d needs no push pass; a single barrier before its last sweep orders the stores (cg_fuse_push)
+    const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->cg_fuse_push && ctx->p2p_ok && ctx->arena_stride >= n;
+    PeerPtrs pp = peer_ptrs(ctx);
+    if (fuse_push && !ctx->fresh_collective) DSEA_TRY(comm_barrier(ctx, st));          // partners are done reading x's shards
+    DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st, fuse_push ? &pp : nullptr));
+    ctx->guard = ctx->scal + S_DONE;
+    const size_t prof_first = prof_mark(ctx);
+    int status = DSEA_OK;
+    int64_t issued = 0;
+    int slot = 0;
+    bool have_prev = false;
+    bool finished = false;
+    while (!finished) {
+        const int64_t chunk = ctx->cg_check_every;
+        for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
+            prof_guard_key(ctx, 2 * (issued + q));
+            status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st,
+                              fuse_push ? XCH_PREPUSHED_BARRIER : XCH_PUSH);                   // one matvec / iteration
+            if (status == DSEA_OK && proj) status = project(ctx, n, proj, Ad, Ad, st);         // d.Ad is unchanged: d is orthogonal to proj
+            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st, fuse_push ? &pp : nullptr);
+        }
+        if (status != DSEA_OK) break;
+        issued += chunk;
+        status = cg_poll(ctx, slot, st);
+        if (status != DSEA_OK) break;
+        if (have_prev) {      // look at the PREVIOUS chunk's flag while this chunk runs
+            cudaError_t e = cudaEventSynchronize(ctx->ev_poll[slot ^ 1]);
+            if (e != cudaSuccess) { set_error("CG poll failed: %s", cudaGetErrorString(e)); status = DSEA_ERR_CUDA; break; }
+            if (ctx->pinned[8 * (slot ^ 1)] != 0.0) finished = true;
+        }
+        have_prev = true;
+        slot ^= 1;
+        if (issued >= maxit) finished = true;
+    }
+    ctx->guard = nullptr;
+    prof_guard_key(ctx, -1);
+    if (status != DSEA_OK) return status;
+    DSEA_TRY(cg_poll(ctx, slot, st));
+    DSEA_CUDA(cudaStreamSynchronize(st));
+    const double done = ctx->pinned[8 * slot], iters = ctx->pinned[8 * slot + 1], rnorm = ctx->pinned[8 * slot + 2];
+    if (iters_host) *iters_host = (int64_t)iters;
+    // iteration `iters - 1` set the flag in its scalar kernel: its direction update (key 2*(iters-1)+1) and
+    // everything issued afterwards were no-ops
+    prof_retire_guarded(ctx, prof_first, done != 0.0 ? 2 * (int64_t)iters - 1 : INT64_MAX);
+    if (done != 1.0) {        // 2: iteration cap or NaN residual; 0: loop left without the flag (cannot happen)
+        set_error("CG stopped after %lld iterations with |r| = %.3e >= eps = %.3e (CG.py:32 returns silently here)",
+                  (long long)iters, rnorm, eps);
+        return DSEA_ERR_NOCONV;
+    }
+    return DSEA_OK;
+}
+
+
 // ---- Lanczos ----------------------------------------------------------------------------------------
-int64_t dsea_lanczos_work_doubles(const dsea_op* op) { return col_stride(op->n_loc) + dsea_op_work_doubles(op); }
+static inline int64_t col_stride_f32(int64_t n) { return (n + 31) & ~(int64_t)31; }      // floats; 128-byte columns
+
+int64_t dsea_lanczos_work_doubles(const dsea_op* op) {
+    const int64_t nvec = (op->ctx->basis_fp32 && op->kind == DSEA_OP_TFIM) ? 9 : 1;      // fp32 basis: u, r, q + polish (b, delta, r, d, Ad, spare)
+    return nvec * col_stride(op->n_loc) + dsea_op_work_doubles(op);
+}
+
+int64_t dsea_lanczos_basis_doubles(const dsea_op* op, int k) {
+    const int64_t n = op->n_loc;
+    if (op->ctx->basis_fp32 && op->kind == DSEA_OP_TFIM) {
+        const int64_t need = ((int64_t)k * col_stride_f32(n) + 1) / 2;                   // k float columns
+        return need > col_stride(n) ? need : col_stride(n);                              // ... and room for the fp64 q0 on entry
+    }
+    return (int64_t)k * col_stride(n);
+}
+
+__global__ void polish_scalars_kernel(double* scal) {
+    // S_TMP0 = 1 / |x| from S_BETA2 = x.x
+    const double nn = scal[S_BETA2];
+    scal[S_TMP0] = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
+}
+
+__global__ void rayleigh_residual_kernel(const double* __restrict__ x, const double* __restrict__ Ax,
+                                         const double* __restrict__ theta, double* __restrict__ b, int64_t n) {
+    // b = theta x - A x   (right-hand side of the correction equation, orthogonal to x by construction)
+    const double th = *theta;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) b[i] = th * x[i] - Ax[i];
+}
+
+// Jacobi-Davidson polish of an approximate ground state x (any norm), in fp64:
+//   x <- x / |x| ; theta = x.Ax ; solve P (A - theta) P delta = theta x - A x with P = 1 - x x^T (projected CG) ;
+//   x <- (x + delta) / |x + delta| ; theta <- x.Ax.
+// One step is quadratically convergent: the fp32-basis Ritz vector (eigenvector error ~1e-6, residual ~3e-7) comes out
+// with residual ~1e-11 after ~40 CG iterations (measured on the CPU prototype at N = 12 ... 14).
+// work: 7 column strides (Ax, b, delta, CG r / d / Ad) + operator work.
+static int lanczos_polish(dsea_ctx* ctx, const dsea_op* op, const double* param, double* x, double* theta_out,
+                          double* work, double* opwork, cudaStream_t st) {
+    const int64_t n = op->n_loc, ld = col_stride(n);
+    double* Ax = work;
+    double* b = work + ld;
+    double* delta = work + 2 * ld;
+    double* cgwork = work + 3 * ld;               // r, d, Ad (+ operator work right behind, see dsea_lanczos_work_doubles)
+    (void)opwork;
+    const int grid = ctx->num_sms * 8;
+    for (int pass = 0; pass < 2; ++pass) {
+        DSEA_TRY(dot(ctx, n, x, x, ctx->scal + S_BETA2, st));
+        DSEA_TRY(scale_by_inv_sqrt(ctx, n, x, ctx->scal + S_BETA2, st));
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, x, Ax, theta_out, cgwork + 3 * ld, st));      // theta = x . A x
+        if (pass == 1) break;
+        rayleigh_residual_kernel<<<grid, 256, 0, st>>>(x, Ax, theta_out, b, n);
+        count_launch(ctx);
+        DSEA_CUDA(cudaGetLastError());
+        DSEA_CUDA(cudaMemsetAsync(delta, 0, (size_t)n * sizeof(double), st));
+        int64_t iters = 0;
+        const int s = cg_solve_impl(ctx, op, param, theta_out, b, delta, cgwork, ctx->polish_eps, 2000, x, &iters, st);
+        if (s != DSEA_OK && s != DSEA_ERR_NOCONV) return s;
+        ctx->last_polish_iters = iters;
+        DSEA_TRY(axpby(ctx, n, nullptr, delta, nullptr, x, st));                                  // x += delta
+    }
+    return DSEA_OK;
+}
+
+// Lanczos with the fp32 shadow basis (opt-in "basis_fp32", TFIM operators, extreme = "min").
+// Every stored Lanczos vector is q~ = fl32(r / beta), and that rounded vector IS the Lanczos vector: the matvec input
+// (fp64 copy `qcur`), the recurrence terms (read back from the float columns) and the remote shards (the partners
+// round the same r / beta) all use it, so c = Q~^T r0 is exact with respect to the stored basis and only the rounding
+// of each new vector (6e-8) perturbs the Lanczos relation.  The Ritz VALUE of T is then only good to ~1e-9, so the
+// eigenvalue returned is the Rayleigh quotient of the polished Ritz vector (lanczos_polish).
+static int lanczos_fp32_impl(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, double* Qraw, double* work,
+                             double* alpha, double* beta, double* evals, double* evec_min, int64_t* info_host,
+                             cudaStream_t st) {
+    const int64_t n = op->n_loc, ld = col_stride(n), ldq = col_stride_f32(n);
+    float* Q = (float*)Qraw;
+    double* u = work;
+    double* rvec = work + ld;
+    double* qcur = work + 2 * ld;
+    double* polish_work = work + 3 * ld;          // 6 strides
+    double* opwork = work + 9 * ld;
+    // q0 arrives as n doubles at the start of the basis buffer, which column 0 (n floats) overlaps: move it out first
+    DSEA_CUDA(cudaMemcpyAsync(rvec, Qraw, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    lanczos_reset_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    DSEA_TRY(dot(ctx, n, rvec, rvec, ctx->scal + S_BETA2, st));
+    polish_scalars_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    count_launch(ctx);
+    DSEA_TRY(scale_round_store(ctx, n, rvec, ctx->scal + S_TMP0, qcur, Q, st));               // Lanczos.py:53
+    const bool fuse_push = ctx->p2p_ok && ctx->arena_stride >= n;
+    PeerPtrs pp = peer_ptrs(ctx);
+    for (int i = 0; i < k; ++i) {
+        const bool pre = fuse_push && i > 0;
+        DSEA_TRY(apply_op(ctx, op, param, nullptr, qcur, u, ctx->scal + S_ALPHA_L, opwork, st,
+                          pre ? XCH_PREPUSHED : XCH_PUSH, ctx->scal + S_INVBETA, nullptr, nullptr, /*round_remote=*/true));
+        const int m = i + 1;
+        const bool more = (i < k - 1);
+        if (more) {
+            Recurrence rec;
+            rec.qi = Q + (int64_t)i * ldq;
+            rec.qim1 = i > 0 ? Q + (int64_t)(i - 1) * ldq : nullptr;
+            rec.alpha = ctx->scal + S_ALPHA_L;
+            rec.beta = ctx->scal + S_BETAPREV;
+            rec.r0_out = rvec;
+            DSEA_TRY(reorth_dots_f32(ctx, n, ldq, m, Q, u, ctx->cvec, st, &rec));
+            DSEA_TRY(reorth_update_f32(ctx, n, ldq, m, Q, rvec, ctx->cvec, -1.0, rvec, ctx->scal + S_BETA2, st,
+                                       fuse_push ? &pp : nullptr));
+        }
+        lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, alpha, beta, i, more ? 1 : 0);
+        count_launch(ctx);
+        DSEA_CUDA(cudaGetLastError());
+        if (more) DSEA_TRY(scale_round_store(ctx, n, rvec, ctx->scal + S_INVBETA, qcur, Q + (int64_t)m * ldq, st));
+    }
+    double* ymin = ctx->yvec;
+    DSEA_TRY(tridiag_extreme(ctx, k, DSEA_MIN, alpha, beta, ctx->scal + S_KEFF, evals, ymin, ctx->yvec + kMaxK, st));
+    DSEA_TRY(reorth_update_f32(ctx, n, ldq, k, Q, nullptr, ymin, 1.0, evec_min, nullptr, st));
+    DSEA_TRY(lanczos_polish(ctx, op, param, evec_min, evals, polish_work, opwork, st));
+    if (info_host) {
+        DSEA_CUDA(cudaMemcpyAsync(ctx->pinned, ctx->scal + S_KEFF, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DSEA_CUDA(cudaStreamSynchronize(st));
+        const int64_t ke = (int64_t)ctx->pinned[0];
+        info_host[0] = ke > 0 ? ke : k;
+        info_host[1] = (int64_t)ctx->pinned[1];
+    }
+    return DSEA_OK;
+}
 
 int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, int which, double* Q, double* work,
                  double* alpha, double* beta, double* evals, double* evec_min, double* evec_max,
@@ -436,6 +639,10 @@ int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, i
     DSEA_ARG(aligned16(Q) && aligned16(work) && aligned16(evec_min) && aligned16(evec_max), "buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = op->n_loc, ldq = col_stride(n);
+    if (ctx->basis_fp32 && op->kind == DSEA_OP_TFIM) {
+        DSEA_ARG(which == DSEA_MIN && evec_min != nullptr, "the fp32 shadow basis supports extreme = 'min' only");
+        return lanczos_fp32_impl(ctx, op, param, k, Q, work, alpha, beta, evals, evec_min, info_host, st);
+    }
     double* u = work;
     double* opwork = work + ldq;
     DSEA_TRY(lanczos_start_impl(ctx, n, Q, st));
@@ -520,76 +727,11 @@ int dsea_combine(dsea_ctx* ctx, int64_t n_loc, int m, const double* Q, const dou
 // ---- CG -----------------------------------------------------------------------------------------------
 int64_t dsea_cg_work_doubles(const dsea_op* op) { return 3 * col_stride(op->n_loc) + dsea_op_work_doubles(op); }
 
-static int cg_poll(dsea_ctx* ctx, int slot, cudaStream_t st) {
-    DSEA_CUDA(cudaMemcpyAsync(ctx->pinned + 8 * slot, ctx->scal + S_DONE, 3 * sizeof(double),
-                              cudaMemcpyDeviceToHost, st));          // {done, iters, rnorm}
-    DSEA_CUDA(cudaEventRecord(ctx->ev_poll[slot], st));
-    return DSEA_OK;
-}
-
 int dsea_cg(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* b, double* x,
             double* work, double eps, int64_t maxit, int64_t* iters_host, void* stream) {
     DSEA_ARG(ctx && op && b && x && work, "NULL argument");
     DSEA_ARG(aligned16(b) && aligned16(x) && aligned16(work), "buffers must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n = op->n_loc, ld = col_stride(n);
-    double* r = work;
-    double* d = work + ld;
-    double* Ad = work + 2 * ld;
-    double* opwork = work + 3 * ld;
-    if (maxit <= 0) maxit = n;                                                         // CG.py:32
-    DSEA_TRY(cg_setup(ctx, eps, maxit, st));
-    DSEA_TRY(apply_op(ctx, op, param, shift, x, Ad, nullptr, opwork, st));             // CG.py:27
-    // sharded TFIM: the kernels that write the search direction d also store it into the partners' arenas, so the
-    // matvec of d needs no push pass; a single barrier before its last sweep orders the stores (cg_fuse_push)
-    const bool fuse_push = op->kind == DSEA_OP_TFIM && ctx->cg_fuse_push && ctx->p2p_ok && ctx->arena_stride >= n;
-    PeerPtrs pp = peer_ptrs(ctx);
-    if (fuse_push && !ctx->fresh_collective) DSEA_TRY(comm_barrier(ctx, st));          // partners are done reading x's shards
-    DSEA_TRY(cg_init(ctx, n, b, Ad, r, d, st, fuse_push ? &pp : nullptr));
-    ctx->guard = ctx->scal + S_DONE;
-    const size_t prof_first = prof_mark(ctx);
-    int status = DSEA_OK;
-    int64_t issued = 0;
-    int slot = 0;
-    bool have_prev = false;
-    bool finished = false;
-    while (!finished) {
-        const int64_t chunk = ctx->cg_check_every;
-        for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
-            prof_guard_key(ctx, 2 * (issued + q));
-            status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st,
-                              fuse_push ? XCH_PREPUSHED_BARRIER : XCH_PUSH);                   // one matvec / iteration
-            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st, fuse_push ? &pp : nullptr);
-        }
-        if (status != DSEA_OK) break;
-        issued += chunk;
-        status = cg_poll(ctx, slot, st);
-        if (status != DSEA_OK) break;
-        if (have_prev) {      // look at the PREVIOUS chunk's flag while this chunk runs
-            cudaError_t e = cudaEventSynchronize(ctx->ev_poll[slot ^ 1]);
-            if (e != cudaSuccess) { set_error("CG poll failed: %s", cudaGetErrorString(e)); status = DSEA_ERR_CUDA; break; }
-            if (ctx->pinned[8 * (slot ^ 1)] != 0.0) finished = true;
-        }
-        have_prev = true;
-        slot ^= 1;
-        if (issued >= maxit) finished = true;
-    }
-    ctx->guard = nullptr;
-    prof_guard_key(ctx, -1);
-    if (status != DSEA_OK) return status;
-    DSEA_TRY(cg_poll(ctx, slot, st));
-    DSEA_CUDA(cudaStreamSynchronize(st));
-    const double done = ctx->pinned[8 * slot], iters = ctx->pinned[8 * slot + 1], rnorm = ctx->pinned[8 * slot + 2];
-    if (iters_host) *iters_host = (int64_t)iters;
-    // iteration `iters - 1` set the flag in its scalar kernel: its direction update (key 2*(iters-1)+1) and
-    // everything issued afterwards were no-ops
-    prof_retire_guarded(ctx, prof_first, done != 0.0 ? 2 * (int64_t)iters - 1 : INT64_MAX);
-    if (done != 1.0) {        // 2: iteration cap or NaN residual; 0: loop left without the flag (cannot happen)
-        set_error("CG stopped after %lld iterations with |r| = %.3e >= eps = %.3e (CG.py:32 returns silently here)",
-                  (long long)iters, rnorm, eps);
-        return DSEA_ERR_NOCONV;
-    }
-    return DSEA_OK;
+    return cg_solve_impl(ctx, op, param, shift, b, x, work, eps, maxit, nullptr, iters_host, (cudaStream_t)stream);
 }
 
 int dsea_cg_init(dsea_ctx* ctx, int64_t n_loc, const double* b, const double* Ax, double* r, double* d,

@@ -76,8 +76,8 @@ struct PeerPtrs {
 // Three-term recurrence applied in the prologue of reorth pass 1: r0 = u - (*alpha) qi - (*beta) qim1,
 // written to r0_out (qim1 may be NULL for the first step).
 struct Recurrence {
-    const double* qi;
-    const double* qim1;
+    const void* qi;            // basis columns: double or float according to the kernel's basis element type
+    const void* qim1;
     const double* alpha;
     const double* beta;
     double* r0_out;
@@ -143,6 +143,8 @@ struct dsea_ctx {
     int cg_fuse_push = 1;               // CG direction update stores d into the partners' arenas
     int cg_check_every = 16;
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
+    double polish_eps = 1e-10;          // absolute CG tolerance of the Jacobi-Davidson polish (fp32 basis)
+    int64_t last_polish_iters = 0;
     int basis_fp32 = 0;                 // opt-in: Lanczos basis also kept as an fp32 shadow that the reorth passes stream
 };
 
@@ -178,7 +180,7 @@ enum { XCH_PUSH = 0, XCH_PREPUSHED = 1, XCH_PREPUSHED_BARRIER = 2 };
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
                double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st,
                int exchange = XCH_PUSH, const double* remote_scale = nullptr, const double* in_scale = nullptr,
-               double* q_out = nullptr);
+               double* q_out = nullptr, bool round_remote = false);
 bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op);
 int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st);
 int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
@@ -197,6 +199,15 @@ int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double
                   const double* c, double sign, double* r_out, double* norm2_out,
                   cudaStream_t st, const PeerPtrs* peers = nullptr);   // r = u + sign * Q c  (u may be NULL)
 int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, cudaStream_t st);
+// fp32 shadow basis (opt-in "basis_fp32"): the same two passes over float columns with fp64 accumulation, and the
+// normalisation that rounds the new vector to fp32 (q32 = fl32(r * *scale), q64 = the same values widened)
+int reorth_dots_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const float* Q, const double* u, double* c_out,
+                    cudaStream_t st, const Recurrence* rec = nullptr);
+int reorth_update_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const float* Q, const double* u,
+                      const double* c, double sign, double* r_out, double* norm2_out, cudaStream_t st,
+                      const PeerPtrs* peers = nullptr);
+int scale_round_store(dsea_ctx* ctx, int64_t n, const double* r, const double* scale, double* q64, float* q32,
+                      cudaStream_t st);
 // blas1.cu
 int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st);
 int axpby(dsea_ctx* ctx, int64_t n, const double* a, const double* x, const double* b, double* y, cudaStream_t st);

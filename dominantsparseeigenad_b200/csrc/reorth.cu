@@ -2,26 +2,52 @@
 // Ritz-vector GEMV (K5).  Replaces `r -= Q[:, :i] (Q[:, :i]^T r)` (Lanczos.py:66) and
 // `Qk @ eigvectors` (Lanczos.py:99).
 //
-// Layout: the basis is COLUMN-contiguous (column j at Q + j*ldq, ldq a multiple of 16 doubles), the
-// opposite of the reference's row-major (n, k) tensor whose column views have stride k.
+// Layout: the basis is COLUMN-contiguous (column j at Q + j*ldq), the opposite of the reference's
+// row-major (n, k) tensor whose column views have stride k.
 //
-//   pass 1 (reorth_dots)   c = Q[:, :m]^T u        reads 8 n (m + 1) bytes
-//   pass 2 (reorth_update) r = u - Q[:, :m] c      reads 8 n (m + 1), writes 8 n; |r|^2 in the epilogue
+//   pass 1 (reorth_dots)   c = Q[:, :m]^T u        reads s n m + 8 n bytes        (s = bytes per basis element)
+//   pass 2 (reorth_update) r = u - Q[:, :m] c      reads s n m + 8 n, writes 8 n; |r|^2 in the epilogue
 //
-// Both are HBM-streaming kernels: a CTA owns 1024-row tiles (4 rows per thread as two 16 B vectors),
-// keeps the u / r tile in registers and streams the m column segments past it with >= 16 independent
-// 16 B loads in flight per thread.  Pass 2 walks the tiles in the opposite order to pass 1 so that it
-// starts on the part of Q that pass 1 left in the 126 MB L2.
+// Both are HBM-streaming kernels: a CTA owns tiles of 256 x 2 x (16 / s) rows (two 16-byte basis vectors per
+// thread and column), keeps the u / r tile in registers as fp64 and streams the m column segments past it
+// with >= 16 independent 16 B loads in flight per thread.  Pass 2 walks the tiles in the opposite order to
+// pass 1 so that it starts on the part of Q that pass 1 left in the 126 MB L2.
 // Reductions are deterministic: per-warp shared-memory accumulators -> per-CTA partials (fixed order)
-// -> one finalize CTA per column (fixed order) -> NCCL allreduce when sharded.
+// -> one finalize CTA per column (fixed order) -> cross-rank sum when sharded.
+//
+// Basis element type.  double (s = 8) is the reference's precision (Lanczos.py:43,49).  float (s = 4) is the
+// opt-in shadow basis ("basis_fp32"): the stored Lanczos vectors are rounded to fp32 — and those rounded values
+// ARE the Lanczos vectors (the matvec input and the recurrence use them too, see api.cu) — while every
+// accumulation stays fp64.  It halves the dominant HBM traffic and the basis footprint (N = 30, k = 200 on 8 GPUs:
+// 107 GB per GPU instead of 215 GB); the eigenpair is then polished in fp64 (api.cu, lanczos_polish).
 #include "common.cuh"
 
 namespace dsea {
 
 constexpr int kRThreads = 256;
-constexpr int kRowsPerThread = 4;
-constexpr int kTileRows = kRThreads * kRowsPerThread;   // 1024
 constexpr int kJB = 8;                                   // columns per register chunk in pass 1
+
+template <typename QT> struct QTraits;
+template <> struct QTraits<double> {
+    static constexpr int R = 2;                          // rows per 16-byte vector
+    typedef double2 V;
+    static __device__ __forceinline__ V load(const double* p) { return ldg2_stream(p); }
+    static __device__ __forceinline__ void widen(const V& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+};
+template <> struct QTraits<float> {
+    static constexpr int R = 4;
+    typedef float4 V;
+    static __device__ __forceinline__ V load(const float* p) {
+        V r;
+        asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                     : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void widen(const V& v, double (&o)[4]) {
+        o[0] = (double)v.x; o[1] = (double)v.y; o[2] = (double)v.z; o[3] = (double)v.w;
+    }
+};
 
 // Sum kJB=8 per-lane values across the warp with 9 shuffles; afterwards every lane holds the warp
 // total of value index ((lane >> 2) & 7).
@@ -55,10 +81,24 @@ __device__ __forceinline__ double warp_reduce8(double (&v)[8], int lane) {
     return v[0];
 }
 
+// Three-term recurrence applied in the prologue of pass 1 (typed view of `Recurrence`).
+template <typename QT>
+struct RecT {
+    const QT* qi;
+    const QT* qim1;
+    const double* alpha;
+    const double* beta;
+    double* r0_out;
+};
+
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
+template <typename QT>
 __global__ void __launch_bounds__(kRThreads, 2)
-reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
-                   double* __restrict__ partials, const Recurrence rec) {
+reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
+                   double* __restrict__ partials, const RecT<QT> rec) {
+    typedef QTraits<QT> TR;
+    constexpr int R = TR::R;
+    constexpr int kTileRows = kRThreads * 2 * R;
     extern __shared__ double wacc[];                 // [8 warps][m] per-warp accumulators
     // three-term recurrence folded into the prologue: r0 = u - alpha q_i - beta q_{i-1}  (Lanczos.py:61)
     const double ra = rec.qi ? *rec.alpha : 0.0;
@@ -70,64 +110,90 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
     const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t r0 = t * kTileRows + 2 * threadIdx.x;          // rows r0, r0+1
-        const int64_t r1 = r0 + kTileRows / 2;                        // rows r1, r1+1
+        const int64_t rA = t * kTileRows + R * threadIdx.x;           // rows rA .. rA+R-1
+        const int64_t rB = rA + kTileRows / 2;                        // rows rB .. rB+R-1
         const bool full = (t + 1) * kTileRows <= n;
-        double2 u0, u1;
+        double ua[R], ub[R];
         if (full) {
-            u0 = ldg2(u + r0);
-            u1 = ldg2(u + r1);
+#pragma unroll
+            for (int e = 0; e < R; e += 2) {
+                const double2 x = ldg2(u + rA + e), y = ldg2(u + rB + e);
+                ua[e] = x.x; ua[e + 1] = x.y; ub[e] = y.x; ub[e + 1] = y.y;
+            }
         } else {
-            u0.x = r0 < n ? u[r0] : 0.0;
-            u0.y = r0 + 1 < n ? u[r0 + 1] : 0.0;
-            u1.x = r1 < n ? u[r1] : 0.0;
-            u1.y = r1 + 1 < n ? u[r1 + 1] : 0.0;
+#pragma unroll
+            for (int e = 0; e < R; ++e) {
+                ua[e] = rA + e < n ? u[rA + e] : 0.0;
+                ub[e] = rB + e < n ? u[rB + e] : 0.0;
+            }
         }
         if (rec.qi) {
             if (full) {
-                const double2 q0 = ldg2(rec.qi + r0), q1 = ldg2(rec.qi + r1);
-                u0.x -= ra * q0.x; u0.y -= ra * q0.y; u1.x -= ra * q1.x; u1.y -= ra * q1.y;
-                if (rec.qim1) {
-                    const double2 p0 = ldg2(rec.qim1 + r0), p1 = ldg2(rec.qim1 + r1);
-                    u0.x -= rb * p0.x; u0.y -= rb * p0.y; u1.x -= rb * p1.x; u1.y -= rb * p1.y;
-                }
-                stg2(rec.r0_out + r0, u0);
-                stg2(rec.r0_out + r1, u1);
-            } else {
-                const int64_t rows[4] = {r0, r0 + 1, r1, r1 + 1};
-                double* uv[4] = {&u0.x, &u0.y, &u1.x, &u1.y};
+                double qa[R], qb[R];
+                TR::widen(TR::load(rec.qi + rA), qa);
+                TR::widen(TR::load(rec.qi + rB), qb);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (rows[q] < n) {
-                        *uv[q] -= ra * rec.qi[rows[q]];
-                        if (rec.qim1) *uv[q] -= rb * rec.qim1[rows[q]];
-                        rec.r0_out[rows[q]] = *uv[q];
+                for (int e = 0; e < R; ++e) { ua[e] -= ra * qa[e]; ub[e] -= ra * qb[e]; }
+                if (rec.qim1) {
+                    TR::widen(TR::load(rec.qim1 + rA), qa);
+                    TR::widen(TR::load(rec.qim1 + rB), qb);
+#pragma unroll
+                    for (int e = 0; e < R; ++e) { ua[e] -= rb * qa[e]; ub[e] -= rb * qb[e]; }
+                }
+#pragma unroll
+                for (int e = 0; e < R; e += 2) {
+                    stg2(rec.r0_out + rA + e, make_double2(ua[e], ua[e + 1]));
+                    stg2(rec.r0_out + rB + e, make_double2(ub[e], ub[e + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < R; ++e) {
+                    if (rA + e < n) {
+                        ua[e] -= ra * (double)rec.qi[rA + e];
+                        if (rec.qim1) ua[e] -= rb * (double)rec.qim1[rA + e];
+                        rec.r0_out[rA + e] = ua[e];
                     }
+                    if (rB + e < n) {
+                        ub[e] -= ra * (double)rec.qi[rB + e];
+                        if (rec.qim1) ub[e] -= rb * (double)rec.qim1[rB + e];
+                        rec.r0_out[rB + e] = ub[e];
+                    }
+                }
             }
         }
         for (int j0 = 0; j0 < m; j0 += kJB) {
             double acc[kJB];
             if (full && j0 + kJB <= m) {
-                double2 a[kJB], b[kJB];
+                typename TR::V a[kJB], b[kJB];
 #pragma unroll
                 for (int j = 0; j < kJB; ++j) {
-                    const double* col = Q + (int64_t)(j0 + j) * ldq;
-                    a[j] = ldg2_stream(col + r0);
-                    b[j] = ldg2_stream(col + r1);
+                    const QT* col = Q + (int64_t)(j0 + j) * ldq;
+                    a[j] = TR::load(col + rA);
+                    b[j] = TR::load(col + rB);
                 }
 #pragma unroll
-                for (int j = 0; j < kJB; ++j)
-                    acc[j] = a[j].x * u0.x + a[j].y * u0.y + b[j].x * u1.x + b[j].y * u1.y;
+                for (int j = 0; j < kJB; ++j) {
+                    double wa[R], wb[R];
+                    TR::widen(a[j], wa);
+                    TR::widen(b[j], wb);
+                    double s = wa[0] * ua[0];
+#pragma unroll
+                    for (int e = 1; e < R; ++e) s += wa[e] * ua[e];
+#pragma unroll
+                    for (int e = 0; e < R; ++e) s += wb[e] * ub[e];
+                    acc[j] = s;
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < kJB; ++j) {
                     acc[j] = 0.0;
                     if (j0 + j < m) {
-                        const double* col = Q + (int64_t)(j0 + j) * ldq;
-                        if (r0 < n) acc[j] += col[r0] * u0.x;
-                        if (r0 + 1 < n) acc[j] += col[r0 + 1] * u0.y;
-                        if (r1 < n) acc[j] += col[r1] * u1.x;
-                        if (r1 + 1 < n) acc[j] += col[r1 + 1] * u1.y;
+                        const QT* col = Q + (int64_t)(j0 + j) * ldq;
+#pragma unroll
+                        for (int e = 0; e < R; ++e) {
+                            if (rA + e < n) acc[j] += (double)col[rA + e] * ua[e];
+                            if (rB + e < n) acc[j] += (double)col[rB + e] * ub[e];
+                        }
                     }
                 }
             }
@@ -146,10 +212,14 @@ reorth_dots_kernel(const double* __restrict__ Q, int64_t ldq, const double* __re
 }
 
 // ---- pass 2: r = u + sign * Q[:, :m] c ;  partial |r|^2 ---------------------------------------------
+template <typename QT>
 __global__ void __launch_bounds__(kRThreads, 2)
-reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
+reorth_update_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
                      const double* __restrict__ c, double sign, int64_t n, int m, double* __restrict__ r,
                      double* __restrict__ partials, const PeerPtrs peers) {
+    typedef QTraits<QT> TR;
+    constexpr int R = TR::R;
+    constexpr int kTileRows = kRThreads * 2 * R;
     extern __shared__ double cs[];                   // m coefficients (pre-multiplied by sign)
     __shared__ double red[32];
     for (int j = threadIdx.x; j < m; j += kRThreads) cs[j] = sign * c[j];
@@ -159,70 +229,91 @@ reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __
 
     for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
         const int64_t t = ntiles - 1 - tt;                            // reverse of pass 1 (L2 reuse)
-        const int64_t r0 = t * kTileRows + 2 * threadIdx.x;
-        const int64_t r1 = r0 + kTileRows / 2;
+        const int64_t rA = t * kTileRows + R * threadIdx.x;
+        const int64_t rB = rA + kTileRows / 2;
         const bool full = (t + 1) * kTileRows <= n;
-        double2 x0 = make_double2(0.0, 0.0), x1 = make_double2(0.0, 0.0);
+        double xa[R], xb[R];
+#pragma unroll
+        for (int e = 0; e < R; ++e) xa[e] = xb[e] = 0.0;
         if (full) {
             if (u) {
-                x0 = ldg2(u + r0);
-                x1 = ldg2(u + r1);
+#pragma unroll
+                for (int e = 0; e < R; e += 2) {
+                    const double2 x = ldg2(u + rA + e), y = ldg2(u + rB + e);
+                    xa[e] = x.x; xa[e + 1] = x.y; xb[e] = y.x; xb[e + 1] = y.y;
+                }
             }
             int j = m;                                                // columns also in reverse
             for (; j >= 8; j -= 8) {
-                double2 a[8], b[8];
+                typename TR::V a[8], b[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const double* col = Q + (int64_t)(j - 1 - q) * ldq;
-                    a[q] = ldg2_stream(col + r0);
-                    b[q] = ldg2_stream(col + r1);
+                    const QT* col = Q + (int64_t)(j - 1 - q) * ldq;
+                    a[q] = TR::load(col + rA);
+                    b[q] = TR::load(col + rB);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const double cj = cs[j - 1 - q];
-                    x0.x += cj * a[q].x;
-                    x0.y += cj * a[q].y;
-                    x1.x += cj * b[q].x;
-                    x1.y += cj * b[q].y;
+                    double wa[R], wb[R];
+                    TR::widen(a[q], wa);
+                    TR::widen(b[q], wb);
+#pragma unroll
+                    for (int e = 0; e < R; ++e) { xa[e] += cj * wa[e]; xb[e] += cj * wb[e]; }
                 }
             }
             for (; j >= 1; --j) {
-                const double* col = Q + (int64_t)(j - 1) * ldq;
-                const double2 a = ldg2_stream(col + r0), b = ldg2_stream(col + r1);
+                const QT* col = Q + (int64_t)(j - 1) * ldq;
+                double wa[R], wb[R];
+                TR::widen(TR::load(col + rA), wa);
+                TR::widen(TR::load(col + rB), wb);
                 const double cj = cs[j - 1];
-                x0.x += cj * a.x;
-                x0.y += cj * a.y;
-                x1.x += cj * b.x;
-                x1.y += cj * b.y;
+#pragma unroll
+                for (int e = 0; e < R; ++e) { xa[e] += cj * wa[e]; xb[e] += cj * wb[e]; }
             }
-            stg2(r + r0, x0);
-            stg2(r + r1, x1);
-            for (int pj = 0; pj < peers.n; ++pj) {       // fused exchange: NVLink stores into the partners' arenas
-                stg2(peers.p[pj] + r0, x0);
-                stg2(peers.p[pj] + r1, x1);
+#pragma unroll
+            for (int e = 0; e < R; e += 2) {
+                const double2 va = make_double2(xa[e], xa[e + 1]), vb = make_double2(xb[e], xb[e + 1]);
+                stg2(r + rA + e, va);
+                stg2(r + rB + e, vb);
+                for (int pj = 0; pj < peers.n; ++pj) {   // fused exchange: NVLink stores into the partners' arenas
+                    stg2(peers.p[pj] + rA + e, va);
+                    stg2(peers.p[pj] + rB + e, vb);
+                }
             }
         } else {
-            const int64_t rows[4] = {r0, r0 + 1, r1, r1 + 1};
-            double xv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) xv[q] = (u && rows[q] < n) ? u[rows[q]] : 0.0;
+            for (int e = 0; e < R; ++e) {
+                if (u && rA + e < n) xa[e] = u[rA + e];
+                if (u && rB + e < n) xb[e] = u[rB + e];
+            }
             for (int j = 0; j < m; ++j) {
-                const double* col = Q + (int64_t)j * ldq;
+                const QT* col = Q + (int64_t)j * ldq;
                 const double cj = cs[j];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (rows[q] < n) xv[q] += cj * col[rows[q]];
+                for (int e = 0; e < R; ++e) {
+                    if (rA + e < n) xa[e] += cj * (double)col[rA + e];
+                    if (rB + e < n) xb[e] += cj * (double)col[rB + e];
+                }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (rows[q] < n) {
-                    r[rows[q]] = xv[q];
-                    for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][rows[q]] = xv[q];
+            for (int e = 0; e < R; ++e) {
+                if (rA + e < n) {
+                    r[rA + e] = xa[e];
+                    for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][rA + e] = xa[e];
+                } else {
+                    xa[e] = 0.0;
                 }
-            x0 = make_double2(xv[0], xv[1]);
-            x1 = make_double2(xv[2], xv[3]);
+                if (rB + e < n) {
+                    r[rB + e] = xb[e];
+                    for (int pj = 0; pj < peers.n; ++pj) peers.p[pj][rB + e] = xb[e];
+                } else {
+                    xb[e] = 0.0;
+                }
+            }
         }
-        nrm += x0.x * x0.x + x0.y * x0.y + x1.x * x1.x + x1.y * x1.y;
+#pragma unroll
+        for (int e = 0; e < R; ++e) nrm += xa[e] * xa[e] + xb[e] * xb[e];
     }
     if (partials) {
         const double tot = block_sum(nrm, red);
@@ -231,8 +322,8 @@ reorth_update_kernel(const double* __restrict__ Q, int64_t ldq, const double* __
 }
 
 // `m` = partial sums each CTA writes (pass 1: one per column): grid * m must fit ctx->partials.
-static inline int reorth_grid(const dsea_ctx* ctx, int64_t n, int m = 1) {
-    const int64_t ntiles = (n + kTileRows - 1) / kTileRows;
+static inline int reorth_grid(const dsea_ctx* ctx, int64_t n, int tile_rows, int m = 1) {
+    const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
     int64_t cap = (int64_t)ctx->num_sms * ctx->reorth_ctas_per_sm;
     if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
     if (cap * m > kPartialDoubles) cap = kPartialDoubles / m;
@@ -240,47 +331,113 @@ static inline int reorth_grid(const dsea_ctx* ctx, int64_t n, int m = 1) {
     return (int)(ntiles < cap ? ntiles : cap);
 }
 
-int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, double* c_out,
-                cudaStream_t st, const Recurrence* rec) {
-    const int grid = reorth_grid(ctx, n, m);
+template <typename QT>
+static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT* Q, const double* u, double* c_out,
+                         cudaStream_t st, const Recurrence* rec) {
+    const int grid = reorth_grid(ctx, n, kRThreads * 2 * QTraits<QT>::R, m);
     const size_t smem = (size_t)8 * m * sizeof(double);
     DSEA_ARG(smem <= 200 * 1024, "too many Lanczos vectors for the reorth accumulators");
     static size_t smem_set = 0;
     if (smem > 48 * 1024 && smem > smem_set) {
-        DSEA_CUDA(cudaFuncSetAttribute(reorth_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DSEA_CUDA(cudaFuncSetAttribute(reorth_dots_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_set = 200 * 1024;
     }
-    const int tok =
-        prof_begin(ctx, PK_REORTH_DOTS, 8.0 * (double)n * (m + 1 + (rec ? 3 : 0)), st);
-    Recurrence rc;
+    const double s = (double)sizeof(QT);
+    const int tok = prof_begin(ctx, PK_REORTH_DOTS, (double)n * (s * m + 8.0 + (rec ? 2.0 * s + 8.0 : 0.0)), st);
+    RecT<QT> rc;
     rc.qi = rc.qim1 = nullptr;
     rc.alpha = rc.beta = nullptr;
     rc.r0_out = nullptr;
-    if (rec) rc = *rec;
-    reorth_dots_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, rc);
+    if (rec) {
+        rc.qi = (const QT*)rec->qi;
+        rc.qim1 = (const QT*)rec->qim1;
+        rc.alpha = rec->alpha;
+        rc.beta = rec->beta;
+        rc.r0_out = rec->r0_out;
+    }
+    reorth_dots_kernel<QT><<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, rc);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return finalize_reduce(ctx, grid, m, c_out, st);
 }
 
-int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, const double* c,
-                  double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
-    const int grid = reorth_grid(ctx, n);
+template <typename QT>
+static int reorth_update_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT* Q, const double* u, const double* c,
+                           double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
+    const int grid = reorth_grid(ctx, n, kRThreads * 2 * QTraits<QT>::R);
     const size_t smem = (size_t)m * sizeof(double);
-    const int tok =
-        prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, 8.0 * (double)n * (m + (u ? 2 : 1)), st);
+    const double s = (double)sizeof(QT);
+    const int tok = prof_begin(ctx, u ? PK_REORTH_UPDATE : PK_RITZ, (double)n * (s * m + (u ? 16.0 : 8.0)), st);
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
-    reorth_update_kernel<<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
-                                                       norm2_out ? ctx->partials : nullptr, pp);
+    reorth_update_kernel<QT><<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
+                                                           norm2_out ? ctx->partials : nullptr, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (norm2_out) {
         DSEA_TRY(finalize_reduce(ctx, grid, 1, norm2_out, st));
     }
+    return DSEA_OK;
+}
+
+int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, double* c_out,
+                cudaStream_t st, const Recurrence* rec) {
+    return reorth_dots_t<double>(ctx, n, ldq, m, Q, u, c_out, st, rec);
+}
+
+int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, const double* c,
+                  double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
+    return reorth_update_t<double>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers);
+}
+
+int reorth_dots_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float* Q, const double* u, double* c_out,
+                    cudaStream_t st, const Recurrence* rec) {
+    return reorth_dots_t<float>(ctx, n, ldq, m, Q, u, c_out, st, rec);
+}
+
+int reorth_update_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float* Q, const double* u, const double* c,
+                      double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
+    return reorth_update_t<float>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers);
+}
+
+// ---- K3 for the fp32 shadow basis: q = fl32(r * s) stored twice ---------------------------------------------------
+// q32 receives the rounded vector (the basis column), q64 the same values widened (the next matvec's input).
+__global__ void __launch_bounds__(256) scale_round_kernel(const double* __restrict__ r, const double* __restrict__ ps,
+                                                          double* __restrict__ q64, float* __restrict__ q32, int64_t n) {
+    const double s = *ps;
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const double2 a = ldg2(r + 4 * i), b = ldg2(r + 4 * i + 2);
+        float4 f;
+        f.x = (float)(a.x * s); f.y = (float)(a.y * s); f.z = (float)(b.x * s); f.w = (float)(b.y * s);
+        *reinterpret_cast<float4*>(q32 + 4 * i) = f;
+        stg2(q64 + 4 * i, make_double2((double)f.x, (double)f.y));
+        stg2(q64 + 4 * i + 2, make_double2((double)f.z, (double)f.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t i = n4 * 4; i < n; ++i) {
+            const float f = (float)(r[i] * s);
+            q32[i] = f;
+            q64[i] = (double)f;
+        }
+    }
+}
+
+int scale_round_store(dsea_ctx* ctx, int64_t n, const double* r, const double* scale, double* q64, float* q32,
+                      cudaStream_t st) {
+    int64_t want = (n / 4 + 256 * 4 - 1) / (256 * 4);
+    const int64_t cap = (int64_t)ctx->num_sms * 8;
+    if (want < 1) want = 1;
+    const int grid = (int)(want < cap ? want : cap);
+    const int tok = prof_begin(ctx, PK_NORMALISE, 20.0 * (double)n, st);
+    scale_round_kernel<<<grid, 256, 0, st>>>(r, scale, q64, q32, n);
+    prof_end(ctx, tok, st);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
 }
 

@@ -66,6 +66,7 @@ struct SweepParams {
     int no_diag;            // 1: drop the diagonal (u = -g * flip sum), used for dH/dg
     int use_tma;            // 1: stage contiguous tiles with cp.async.bulk + mbarrier (pipelined kernel only)
     int l2_prefetch;        // 1: prefetch.global.L2 the next tile's epilogue operands
+    int round_remote;       // 1: remote terms are fl32(remote_scale * y): the partner's fp32-rounded Lanczos vector
 };
 
 __device__ __forceinline__ double tfim_diag_dev(uint64_t s, int N, uint64_t mask) {
@@ -139,8 +140,13 @@ __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const Swee
                 double r0 = 0.0, r1 = 0.0;
                 for (int j = 0; j < p.nrecv; ++j) {
                     const double2 y = ldg2(p.recv + (uint64_t)j * p.recv_stride + gi);
-                    r0 += y.x;
-                    r1 += y.y;
+                    if (p.round_remote) {
+                        a0 += (double)(float)(rscale * y.x);
+                        a1 += (double)(float)(rscale * y.y);
+                    } else {
+                        r0 += y.x;
+                        r1 += y.y;
+                    }
                 }
                 a0 += rscale * r0;
                 a1 += rscale * r1;
@@ -359,8 +365,9 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
             for (int j = 0; j < PAIRS; ++j) y[j] = ldg2(slot + gidx(base, eoff(j)));
 #pragma unroll
             for (int j = 0; j < PAIRS; ++j) {
-                a[j].x += rscale * y[j].x;
-                a[j].y += rscale * y[j].y;
+                const double t0 = rscale * y[j].x, t1 = rscale * y[j].y;
+                a[j].x += p.round_remote ? (double)(float)t0 : t0;
+                a[j].y += p.round_remote ? (double)(float)t1 : t1;
             }
         }
         if (MODE == MODE_ADJ) {
@@ -534,7 +541,8 @@ bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op) {
 //   XCH_PREPUSHED_BARRIER  as above but no collective followed the producer: one barrier before the last sweep.
 static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const double* g, const double* shift,
                     const double* v, double* u, const double* w, double* dot_out, double* work, cudaStream_t st,
-                    int exchange, const double* remote_scale, const double* in_scale, double* q_out) {
+                    int exchange, const double* remote_scale, const double* in_scale, double* q_out,
+                    bool round_remote = false) {
     Sweep sw[kMaxSweeps];
     const int L = op->L;
     const int Tmax = clamp_tile_bits(ctx->tfim_tile_bits);
@@ -591,6 +599,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.no_diag = (!mode_adj && g == nullptr) ? 1 : 0;
         p.use_tma = (ctx->tfim_tma && sw[j].c == sw[j].T && (((uintptr_t)v) & 127u) == 0) ? 1 : 0;
         p.l2_prefetch = ctx->tfim_l2_prefetch;
+        p.round_remote = (round_remote && p2p && prepushed) ? 1 : 0;
         p.nrecv = last ? nrecv : 0;
         p.rank_off = (uint64_t)ctx->rank << L;
         p.n_loc = (uint64_t)op->n_loc;
@@ -637,10 +646,10 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
 
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
                double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st, int exchange,
-               const double* remote_scale, const double* in_scale, double* q_out) {
+               const double* remote_scale, const double* in_scale, double* q_out, bool round_remote) {
     // with a fused input scale the dot partner is the SCALED input, which the kernel holds in registers (w == v)
     return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st, exchange, remote_scale,
-                    in_scale, q_out);
+                    in_scale, q_out, round_remote);
 }
 
 // u = (dH/dg) v: the same sweeps with g = 1 and the diagonal dropped (g == nullptr selects this).

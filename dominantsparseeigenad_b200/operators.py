@@ -157,7 +157,8 @@ class NativeOperator:
         """Device-resident k-step Lanczos + tridiagonal eigensolve + Ritz vectors (Lanczos.py:3-105)."""
         rt, lib = self.rt, self.rt.lib
         n, ldq = self.n_loc, self.rt.col_stride(self.n_loc)
-        Q = empty(k * ldq, self.device)
+        # k * ldq doubles, or k float columns under the opt-in fp32 shadow basis (runtime.set_basis_precision)
+        Q = empty(int(lib.dsea_lanczos_basis_doubles(self.handle, k)), self.device)
         runtime.start_vector(n, "lanczos", out=Q[:n])
         work = empty(int(lib.dsea_lanczos_work_doubles(self.handle)), self.device)
         alpha, beta = empty(k, self.device), empty(k, self.device)
@@ -169,7 +170,8 @@ class NativeOperator:
         _lib.check(lib.dsea_lanczos(rt.handle, self.handle, keep[0], k, which, ptr(Q), ptr(work), ptr(alpha),
                                     ptr(beta), ptr(evals), ptr(vmin), ptr(vmax), info, stream_ptr()))
         runtime.stats["lanczos_calls"] += 1
-        return evals, vmin, vmax, {"Q": Q, "ldq": ldq, "alpha": alpha, "beta": beta,
+        fp32 = Q.numel() != k * ldq
+        return evals, vmin, vmax, {"Q": Q, "ldq": ldq, "alpha": alpha, "beta": beta, "basis": "fp32" if fp32 else "fp64",
                                    "k_eff": int(info[0]) if info else None}
 
     def cg(self, param, shift: Optional[torch.Tensor], b: torch.Tensor, x0: torch.Tensor,

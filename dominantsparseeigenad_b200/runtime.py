@@ -94,10 +94,23 @@ def context() -> Context:
         for key, env in (("tfim_tile_bits", "DSEA_TFIM_TILE_BITS"), ("tfim_run_bits", "DSEA_TFIM_RUN_BITS"),
                          ("cg_check_every", "DSEA_CG_CHECK_EVERY"), ("reorth_ctas_per_sm", "DSEA_REORTH_CTAS"),
                          ("p2p", "DSEA_P2P"), ("tfim_pipeline", "DSEA_TFIM_PIPELINE"),
-                         ("mailbox", "DSEA_MAILBOX"), ("tfim_tma", "DSEA_TFIM_TMA")):
+                         ("mailbox", "DSEA_MAILBOX"), ("tfim_tma", "DSEA_TFIM_TMA"), ("basis_fp32", "DSEA_BASIS_FP32"),
+                         ("tfim_direct", "DSEA_TFIM_DIRECT"), ("tfim_fuse_scale", "DSEA_TFIM_FUSE_SCALE"),
+                         ("cg_fuse_push", "DSEA_CG_FUSE_PUSH"), ("tfim_pipe_threads", "DSEA_TFIM_PIPE_THREADS"),
+                         ("tfim_generic_min_operands", "DSEA_TFIM_GENERIC_MIN_OPERANDS")):
             if os.environ.get(env):
                 _ctx.set_option(key, int(os.environ[env]))
     return _ctx
+
+
+def set_basis_precision(kind: str) -> None:
+    """"fp64" (default; the reference's precision, Lanczos.py:43,49) or "fp32": opt-in shadow basis for native TFIM
+    operators — the Lanczos vectors are stored rounded to fp32 (half the HBM traffic of the re-orthogonalisation and
+    half the footprint), every accumulation stays fp64, and the eigenpair is polished in fp64 by one
+    Jacobi-Davidson step, so E0 / psi0 / gradients keep the tolerances of the fp64 path (tests/test_gpu_parity.py)."""
+    if kind not in ("fp64", "fp32"):
+        raise ValueError("basis precision must be 'fp64' or 'fp32'")
+    context().set_option("basis_fp32", 1 if kind == "fp32" else 0)
 
 
 def stream_ptr() -> int:

@@ -90,6 +90,16 @@ def main():
                 print("DIAG chiF", world, rt.p2p_enabled(), -d2.item(), achi, d1.item(),
                       dsea.runtime.stats["cg_iters"][-4:], flush=True)
     assert rel(-d2logF.item(), achi) < 1e-6, (-d2logF.item(), achi)
+    # opt-in fp32 shadow basis on the sharded path (remote shards are rounded exactly like the local vector)
+    dsea.runtime.set_basis_precision("fp32")
+    m32 = dsea.TFIM(N)
+    m32.g = torch.tensor([g], dtype=torch.float64, device=dev, requires_grad=True)
+    dsea.symeig.setDominantSparseSymeig(m32.H, m32.Hadjoint_to_gadjoint)
+    E32, psi32 = dsea.symeig.DominantSparseSymeig.apply(m32.g, k, m32.dim, dev)
+    dE32, = torch.autograd.grad(E32, m32.g)
+    dsea.runtime.set_basis_precision("fp64")
+    assert rel(E32.item(), aE0) < 1e-10 and rel(dE32.item(), adE0) < 1e-6, (E32.item(), aE0, dE32.item(), adE0)
+    assert 1 - abs(dsea.dot(psi32.detach(), psi0.detach()).item()) < 1e-8
     # the oracle-free identities bench.py asserts in every multi-GPU run (each spin bit, remote ones included)
     from dominantsparseeigenad_b200 import selfcheck
     sc = selfcheck.run()

@@ -797,3 +797,65 @@ def test_start_vector_stream_restarts_with_the_seed(dsea):
     a2 = dsea.runtime.start_vector(1000, "lanczos").clone()
     b2 = dsea.runtime.start_vector(1000, "lanczos").clone()
     assert torch.equal(a, a2) and torch.equal(b, b2) and not torch.equal(a, b) and not torch.equal(a, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# opt-in fp32 shadow basis (capacity for N = 30, k = 200; half the reorth traffic)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,k,g", [(16, 200, 1.0), (16, 200, 1.5), (20, 100, 1.25), (13, 150, 1.0)])
+def test_fp32_shadow_basis_keeps_the_fp64_tolerances(dsea, N, k, g):
+    """Lanczos vectors stored rounded to fp32 + one fp64 Jacobi-Davidson polish: E0 to 1e-10, overlap with the
+    fp64-basis eigenvector >= 1 - 1e-8, dE0 / d2E0 / chi_F to 1e-6 — the north-star tolerances — and an eigen-residual
+    no worse than the fp64 path's."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    ex = tfim_exact(N, g)
+    E64, dE64, d2E64, psi64 = _tfim_E0_family(dsea, N, g, k)
+    dsea.runtime.set_basis_precision("fp32")
+    try:
+        E32, dE32, d2E32, psi32 = _tfim_E0_family(dsea, N, g, k)
+        chif = _tfim_chif(dsea, N, g, k)
+        m = dsea.TFIM(N)
+        m.g = cuda([g])
+        resid32 = (m.H(psi32) - E32 * psi32).norm().item()
+    finally:
+        dsea.runtime.set_basis_precision("fp64")
+    assert rel(E32, ex.E0) < EVAL_RTOL and rel(E32, E64) < EVAL_RTOL
+    assert 1 - abs(torch.dot(psi32, psi64).item()) < OVERLAP_TOL
+    assert abs(psi32.norm().item() - 1.0) < 1e-12
+    assert rel(dE32, ex.dE0) < GRAD_RTOL and rel(d2E32, ex.d2E0) < GRAD_RTOL and rel(chif, ex.chiF) < GRAD_RTOL
+    assert resid32 < 1e-8, resid32
+
+
+def test_fp32_shadow_basis_full_size_N24_k200(dsea):
+    """Config 3's size with the compressed basis (13.4 GB instead of 26.8 GB): E0, dE0/dg against the closed forms."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    N, k, g = 24, 200, 1.0
+    ex = tfim_exact(N, g)
+    dsea.runtime.set_basis_precision("fp32")
+    try:
+        m = dsea.TFIM(N)
+        m.g = torch.tensor([g], dtype=F64, device="cuda", requires_grad=True)
+        dsea.symeig.setDominantSparseSymeig(m.H, m.Hadjoint_to_gadjoint)
+        E0, psi0 = dsea.symeig.DominantSparseSymeig.apply(m.g, k, m.dim, torch.device("cuda"))
+        dE0, = torch.autograd.grad(E0, m.g)
+        resid = (m.H(psi0.detach()) - E0.detach() * psi0.detach()).norm().item()
+    finally:
+        dsea.runtime.set_basis_precision("fp64")
+    assert rel(E0.item(), ex.E0) < EVAL_RTOL and rel(dE0.item(), ex.dE0) < GRAD_RTOL and resid < 1e-8
+    torch.cuda.empty_cache()
+
+
+def test_fp32_shadow_basis_is_min_only_and_tfim_only(dsea):
+    from dominantsparseeigenad_b200 import _lib
+    dsea.runtime.set_basis_precision("fp32")
+    try:
+        m = dsea.TFIM(10)
+        m.g = cuda([1.0])
+        with pytest.raises(_lib.DseaError):
+            dsea.Lanczos.symeigLanczos(m.H, 40, device=torch.device("cuda"), extreme="both", sparse=True, dim=m.dim)
+        A = torch.randn(64, 64, dtype=F64, device="cuda")
+        A = A + A.T
+        lo, v = dsea.Lanczos.symeigLanczos(A, 64, extreme="min")       # dense operators keep the fp64 basis
+        assert rel(lo.item(), torch.linalg.eigvalsh(A)[0].item()) < EVAL_RTOL
+    finally:
+        dsea.runtime.set_basis_precision("fp64")
