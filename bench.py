@@ -438,7 +438,8 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by scripts/ncu_traffic.py from one `ncu --set full` capture
         if os.path.exists(tpath):
             try:
-                recs = [r for kname, v in json.load(open(tpath)).items() if "reorth_update_kernel" in kname for r in v]
+                want = "reorth_update_kernel<float>" if args.basis == "fp32" else "reorth_update_kernel<double>"
+                recs = [r for kname, v in json.load(open(tpath)).items() if want in kname for r in v]
                 if recs:
                     ratio = sum(r["traffic_over_algorithmic"] for r in recs) / len(recs)
                     traffic = ratio * dom["algorithmic_bytes_per_step"] / dom["launches_per_step"]
