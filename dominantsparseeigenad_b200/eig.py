@@ -28,6 +28,34 @@ from . import _lib, runtime
 from .operators import DenseOperator
 from .runtime import F64, context, dev_vec, empty, ptr, stream_ptr
 
+
+# -------------------------------------------------------------------------------------------------
+# level-1 pieces through libdsea (deterministic two-stage reductions; results stay on the device)
+# -------------------------------------------------------------------------------------------------
+def _dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a . b as a 1-element device tensor (dsea_dot); no host synchronisation."""
+    rt = context()
+    out = torch.empty(1, dtype=F64, device=rt.device)
+    _lib.check(rt.lib.dsea_dot(rt.handle, a.numel(), ptr(a), ptr(b), out.data_ptr(), stream_ptr()))
+    return out
+
+
+def _axpby(a, x: torch.Tensor, b, y: torch.Tensor) -> torch.Tensor:
+    """y <- a x + b y in place (dsea_axpby); a, b are 1-element device tensors, python floats or None (= 1)."""
+    rt = context()
+    def dev_scalar(s):
+        if s is None or isinstance(s, torch.Tensor):
+            return s
+        return torch.tensor([float(s)], dtype=F64, device=rt.device)
+    a_, b_ = dev_scalar(a), dev_scalar(b)
+    _lib.check(rt.lib.dsea_axpby(rt.handle, y.numel(), None if a_ is None else a_.data_ptr(), ptr(x),
+                                 None if b_ is None else b_.data_ptr(), ptr(y), stream_ptr()))
+    return y
+
+
+def _normalised(x: torch.Tensor) -> torch.Tensor:
+    return _axpby(0.0, x, torch.rsqrt(_dot(x, x)), x)          # x <- x / |x| (one reduction + one pass, no sync)
+
 GMRES_RTOL = 1e-12      # eig.py:54,57
 GMRES_ATOL = 1e-12
 EIG_RTOL = 1e-13        # ARPACK is called with tol=0 (machine precision)
@@ -110,7 +138,7 @@ def dominant_eigpair(apply, n: int, k: int, which: str = "LM"):
         import warnings
         warnings.warn(f"restarted Arnoldi(k={k}) stopped after {MAX_RESTARTS} restarts with residual {resid:.3e}",
                       _lib.ConvergenceWarning, stacklevel=2)
-    x = x / torch.sqrt(torch.dot(x, x))
+    x = _normalised(x)
     # reproducible sign: largest-magnitude component positive
     if x[torch.argmax(x.abs())] < 0:
         x = -x
@@ -123,7 +151,7 @@ def gmres_solve(apply, b: torch.Tensor, restart: int = 64, rtol: float = GMRES_R
     rt = context()
     n = b.numel()
     b = dev_vec(b, rt.device)
-    bnorm = float(torch.sqrt(torch.dot(b, b)).item())
+    bnorm = float(torch.sqrt(_dot(b, b)).item())
     x = torch.zeros(n, dtype=F64, device=rt.device)
     target = max(rtol * bnorm, atol)
     if bnorm <= target:
@@ -139,8 +167,8 @@ def gmres_solve(apply, b: torch.Tensor, restart: int = 64, rtol: float = GMRES_R
         rhs[0, 0] = beta
         y = torch.linalg.lstsq(Hbar[:mm + 1, :mm], rhs, driver="gelsd").solution[:, 0]
         x = _combine(Q, n, mm, y, x)
-        r = b - apply(x)
-        rnorm = float(torch.sqrt(torch.dot(r, r)).item())
+        r = _axpby(-1.0, apply(x), None, b.clone())                        # r = b - A x
+        rnorm = float(torch.sqrt(_dot(r, r)).item())                       # the one host sync of the cycle
         if rnorm <= target:
             break
     else:
@@ -173,7 +201,7 @@ def _callable_apply(A, n: int, shift: float = 0.0):
                 return dev_vec(A(v), rt.device)
     if shift == 0.0:
         return base
-    return lambda v: base(v) - shift * v
+    return lambda v: _axpby(-shift, v, None, base(v))                      # (A - shift) v
 
 
 def _triple(apply_A, apply_AT, n, k, which):
@@ -181,21 +209,21 @@ def _triple(apply_A, apply_AT, n, k, which):
     lam_l, l = dominant_eigpair(apply_AT, n, k, which)
     if abs(lam_l - lam) > 1e-8 * max(abs(lam), 1e-300):
         raise RuntimeError(f"left/right dominant eigenvalues disagree: {lam_l} vs {lam}")
-    l = l / torch.dot(l, r)                                               # eig.py:36
+    l = _axpby(0.0, l, 1.0 / _dot(l, r), l)                               # eig.py:36: l^T r = 1
     return lam, l, r
 
 
 def _backward_vectors(apply_A_shifted, apply_AT_shifted, l, r, grad_l, grad_r):
-    b = grad_l - r * torch.dot(l, grad_l)                                 # eig.py:53,139
+    b = _axpby(-_dot(l, grad_l), r, None, grad_l.clone())                 # eig.py:53,139: grad_l - r (l . grad_l)
     lam_l0 = gmres_solve(apply_A_shifted, b)                              # :54,140
-    b = grad_r - l * torch.dot(r, grad_r)                                 # :56,143
+    b = _axpby(-_dot(r, grad_r), l, None, grad_r.clone())                 # :56,143
     lam_r0 = gmres_solve(apply_AT_shifted, b)                             # :57,144
     # Gauge.  (A - lambda) is singular: solutions differ by multiples of its null vector (r, resp. l).
     # scipy's GMRES from x0 = 0 stays inside the Krylov space of b, which lies in range(A - lambda) =
     # l-perp (resp. r-perp), so the reference implicitly returns the solution with l . x = 0 (r . x = 0).
     # We impose that condition explicitly so that it also holds after Krylov breakdown / restarts.
-    lam_l0 = lam_l0 - r * torch.dot(l, lam_l0)
-    lam_r0 = lam_r0 - l * torch.dot(r, lam_r0)
+    lam_l0 = _axpby(-_dot(l, lam_l0), r, None, lam_l0)
+    lam_r0 = _axpby(-_dot(r, lam_r0), l, None, lam_r0)
     return lam_l0, lam_r0
 
 
@@ -231,7 +259,12 @@ class DominantEig(torch.autograd.Function):
         gl, gr = dev_vec(grad_l, rt.device), dev_vec(grad_r, rt.device)
         lam_l0, lam_r0 = _backward_vectors(_dense_apply(op, lam), _dense_apply(opT, lam), l, r, gl, gr)
         ge = dev_vec(grad_eigval.reshape(-1), rt.device)
-        grad_A = ge * l[:, None] * r - l[:, None] * lam_l0 - lam_r0[:, None] * r          # eig.py:58-60
+        # eig.py:58-60 as ONE rank-2 update: grad_A = l (ge r - lam_l0)^T - lam_r0 r^T  (dsea_outer + one fused add)
+        n = l.numel()
+        right = _axpby(ge, r, -1.0, lam_l0.clone())                       # ge r - lam_l0
+        grad_A = torch.empty(n, n, dtype=F64, device=rt.device)
+        _lib.check(rt.lib.dsea_outer(rt.handle, n, 1.0, ptr(l), ptr(right), grad_A.data_ptr(), stream_ptr()))
+        grad_A.addr_(lam_r0, r, alpha=-1.0)
         return grad_A.to(A.device), None, None
 
 

@@ -20,13 +20,10 @@ import dominantsparseeigenad_b200 as dsea  # noqa: E402
 import dominantsparseeigenad_b200.symeig as symeig  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--variant", default="csr", choices=["matrix", "callback", "csr"])
-    ap.add_argument("--N", type=int, default=300)
-    ap.add_argument("--k", type=int, default=300)
-    ap.add_argument("--steps", type=int, default=5)
-    args = ap.parse_args()
+def fit(variant="csr", N=300, k=300, steps=5, verbose=True):
+    """Runs `steps` L-BFGS steps (schrodinger1D.py:101-123) and returns the loss history."""
+    import types
+    args = types.SimpleNamespace(variant=variant, N=N, k=k, steps=steps)
     N, k = args.N, min(args.k, args.N)
     xmin, xmax = -1.0, 1.0
     x = np.linspace(xmin, xmax, num=N, endpoint=False)
@@ -66,10 +63,24 @@ def main():
         loss.backward()
         return loss
 
+    history = []
     for i in range(args.steps):
         t0 = time.time()
         loss = optimizer.step(closure)
-        print(i, loss.item(), f"{time.time() - t0:.2f} s")
+        history.append(loss.item())
+        if verbose:
+            print(i, loss.item(), f"{time.time() - t0:.2f} s")
+    return history
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variant", default="csr", choices=["matrix", "callback", "csr"])
+    ap.add_argument("--N", type=int, default=300)
+    ap.add_argument("--k", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    fit(a.variant, a.N, a.k, a.steps)
 
 
 if __name__ == "__main__":

@@ -51,6 +51,21 @@ def E0_sparseAD(model, k):                                    # E0.py:53-67
     return E0.item() / model.N, dE0.item() / model.N, d2E0.item() / model.N
 
 
+def sweep(N, k, gs, save=""):
+    """E0.py:94-113: the sparse-AD sweep over g; returns rows (g, E0/N, dE0/N, d2E0/N) and optionally writes the
+    .npz file the reference's plot script reads (keys gs, E0s, dE0s, d2E0s)."""
+    model = dsea.TFIM(N)
+    k = min(k, model.dim)
+    rows = []
+    for gv in gs:
+        model.g = torch.tensor([float(gv)], dtype=torch.float64, device=model.device, requires_grad=True)
+        rows.append((float(gv),) + E0_sparseAD(model, k))
+    if save:
+        arr = np.array(rows)
+        np.savez(save, gs=arr[:, 0], E0s=arr[:, 1], dE0s=arr[:, 2], d2E0s=arr[:, 3])
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spins", type=int, default=10)

@@ -17,6 +17,27 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def sweep(N, k, gs, save=""):
+    """chiF.py:65-82: chi_F over a list of g values; returns rows (g, chi_F) (rank-replicated under torchrun)."""
+    import dominantsparseeigenad_b200 as dsea
+    import dominantsparseeigenad_b200.symeig as symeig
+    rt = dsea.runtime.context()
+    model = dsea.TFIM(N)
+    rows = []
+    for gv in gs:
+        model.g = torch.tensor([float(gv)], dtype=torch.float64, device=model.device, requires_grad=True)
+        symeig.setDominantSparseSymeig(model.H, model.Hadjoint_to_gadjoint)                         # chiF.py:46
+        E0, psi0 = symeig.DominantSparseSymeig.apply(model.g, min(k, model.dim), model.dim, model.device)
+        logF = torch.log(dsea.dot(psi0.detach(), psi0))                                             # chiF.py:49
+        dlogF, = torch.autograd.grad(logF, model.g, create_graph=True)
+        d2logF, = torch.autograd.grad(dlogF, model.g)
+        rows.append((float(gv), -d2logF.item()))
+    if save and rt.rank == 0:
+        arr = np.array(rows)
+        np.savez(save, gs=arr[:, 0], chiFs=arr[:, 1])                                               # chiF.py:81-82
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spins", type=int, default=16)
