@@ -104,7 +104,7 @@ def optimise(model: UniformMPS, steps: int, sparse: bool, verbose: bool = True):
 
     for it in range(steps):
         e = opt.step(closure)
-        history.append(float(e))
+        history.append(float(e.detach()))
         if verbose:
             print(f"step {it:3d}  e = {history[-1]:.12f}")
     return history
