@@ -83,12 +83,13 @@ static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0
 static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const double* shift, const double* v,
                     double* u, double* dot_out, double* work, cudaStream_t st, int exchange = XCH_PUSH,
                     const double* remote_scale = nullptr, const double* in_scale = nullptr, double* q_out = nullptr,
-                    bool round_remote = false) {
+                    bool round_remote = false, bool defer_dot = false) {
+    ctx->pending_dot_n = 0;
     switch (op->kind) {
         case DSEA_OP_TFIM:
             DSEA_ARG(param != nullptr, "TFIM operator needs the device scalar g");
             return tfim_apply(ctx, op, param, shift, v, u, nullptr, dot_out, work, st, exchange, remote_scale, in_scale,
-                              q_out, round_remote);
+                              q_out, round_remote, defer_dot);
         case DSEA_OP_CSR:
             return csr_apply(ctx, op, param, shift, v, u, dot_out, st);
         case DSEA_OP_DENSE:
@@ -105,7 +106,21 @@ __global__ void lanczos_reset_kernel(double* scal) {
 }
 
 // alpha[i] = q_i . A q_i (Lanczos.py:55,72); beta[i] = |r| after re-orthogonalisation (:69); flags breakdown once.
-__global__ void lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_beta) {
+// n_alpha / n_beta2 > 0 (one GPU): the kernel first sums the deferred partials itself — alpha with the same sequential
+// sum reorth pass 1 used in its prologue (bit-identical), |r|^2 with a fixed-order block reduction — which replaces two
+// finalize launches per Lanczos step.
+__global__ void __launch_bounds__(256)
+lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_beta, const double* __restrict__ alpha_partials,
+                      int n_alpha, const double* __restrict__ beta2_partials, int n_beta2) {
+    __shared__ double red[32];
+    if (n_beta2 > 0) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n_beta2; j += blockDim.x) s += beta2_partials[j];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) scal[S_BETA2] = s;
+    }
+    if (threadIdx.x != 0) return;
+    if (n_alpha > 0) scal[S_ALPHA_L] = sum_partials_seq(alpha_partials, n_alpha);
     alpha[i] = scal[S_ALPHA_L];
     if (has_beta) {
         const double b2 = scal[S_BETA2];
@@ -147,8 +162,11 @@ static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i
                              bool normalise = true) {
     const int m = i + 1;
     const double* qi = Q + (int64_t)i * ldq;
+    const int n_alpha = alpha_ready ? ctx->pending_dot_n : 0;      // > 0: the matvec deferred its dot epilogue to us
+    ctx->pending_dot_n = 0;
     if (!alpha_ready) DSEA_TRY(dot(ctx, n, qi, u, ctx->scal + S_ALPHA_L, st));
     const bool more = (i < k - 1);
+    int n_beta2 = 0;
     if (more) {
         double* qnext = Q + (int64_t)m * ldq;
         Recurrence rec;
@@ -157,12 +175,17 @@ static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i
         rec.alpha = ctx->scal + S_ALPHA_L;
         rec.beta = ctx->scal + S_BETAPREV;
         rec.r0_out = qnext;
+        rec.alpha_partials = ctx->partials + kDotPartialsOffset;
+        rec.n_alpha = n_alpha;
         DSEA_TRY(reorth_dots(ctx, n, ldq, m, Q, u, ctx->cvec, st, &rec));
         PeerPtrs pp = peer_ptrs(ctx);
         DSEA_TRY(reorth_update(ctx, n, ldq, m, Q, qnext, ctx->cvec, -1.0, qnext, ctx->scal + S_BETA2, st,
-                               push_next ? &pp : nullptr));
+                               push_next ? &pp : nullptr, /*defer_norm=*/true));
+        n_beta2 = ctx->pending_norm_n;
+        ctx->pending_norm_n = 0;
     }
-    lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, alpha, beta, i, more ? 1 : 0);
+    lanczos_record_kernel<<<1, (n_alpha > 0 || n_beta2 > 0) ? 256 : 1, 0, st>>>(
+        ctx->scal, alpha, beta, i, more ? 1 : 0, ctx->partials + kDotPartialsOffset, n_alpha, ctx->partials, n_beta2);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (more && normalise) DSEA_TRY(scale_by_inv_sqrt(ctx, n, Q + (int64_t)m * ldq, ctx->scal + S_BETA2, st));   // :70,75
@@ -309,6 +332,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "cg_check_every")) ctx->cg_check_every = value < 1 ? 1 : (int)value;
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "basis_fp32")) ctx->basis_fp32 = (value != 0);
+    else if (!strcmp(key, "fuse_small")) ctx->fuse_small = (value != 0);
     else if (!strcmp(key, "polish_eps_1e15")) ctx->polish_eps = 1e-15 * (double)(value < 1 ? 1 : value);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);
@@ -468,9 +492,12 @@ static int cg_solve_impl(dsea_ctx* ctx, const dsea_op* op, const double* param, 
         for (int64_t q = 0; q < chunk && status == DSEA_OK; ++q) {
             prof_guard_key(ctx, 2 * (issued + q));
             status = apply_op(ctx, op, param, shift, d, Ad, ctx->scal + S_DAD, opwork, st,
-                              fuse_push ? XCH_PREPUSHED_BARRIER : XCH_PUSH);                   // one matvec / iteration
+                              fuse_push ? XCH_PREPUSHED_BARRIER : XCH_PUSH, nullptr, nullptr, nullptr, false,
+                              /*defer_dot=*/true);                                             // one matvec / iteration
+            const int n_dad = ctx->pending_dot_n;                                              // > 0: summed by the update kernel
+            ctx->pending_dot_n = 0;
             if (status == DSEA_OK && proj) status = project(ctx, n, proj, Ad, Ad, st);         // d.Ad is unchanged: d is orthogonal to proj
-            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st, fuse_push ? &pp : nullptr);
+            if (status == DSEA_OK) status = cg_iterate(ctx, n, x, r, d, Ad, st, fuse_push ? &pp : nullptr, n_dad);
         }
         if (status != DSEA_OK) break;
         issued += chunk;
@@ -598,9 +625,13 @@ static int lanczos_fp32_impl(dsea_ctx* ctx, const dsea_op* op, const double* par
     for (int i = 0; i < k; ++i) {
         const bool pre = fuse_push && i > 0;
         DSEA_TRY(apply_op(ctx, op, param, nullptr, qcur, u, ctx->scal + S_ALPHA_L, opwork, st,
-                          pre ? XCH_PREPUSHED : XCH_PUSH, ctx->scal + S_INVBETA, nullptr, nullptr, /*round_remote=*/true));
+                          pre ? XCH_PREPUSHED : XCH_PUSH, ctx->scal + S_INVBETA, nullptr, nullptr, /*round_remote=*/true,
+                          /*defer_dot=*/true));
+        const int n_alpha = ctx->pending_dot_n;
+        ctx->pending_dot_n = 0;
         const int m = i + 1;
         const bool more = (i < k - 1);
+        int n_beta2 = 0;
         if (more) {
             Recurrence rec;
             rec.qi = Q + (int64_t)i * ldq;
@@ -608,11 +639,16 @@ static int lanczos_fp32_impl(dsea_ctx* ctx, const dsea_op* op, const double* par
             rec.alpha = ctx->scal + S_ALPHA_L;
             rec.beta = ctx->scal + S_BETAPREV;
             rec.r0_out = rvec;
+            rec.alpha_partials = ctx->partials + kDotPartialsOffset;
+            rec.n_alpha = n_alpha;
             DSEA_TRY(reorth_dots_f32(ctx, n, ldq, m, Q, u, ctx->cvec, st, &rec));
             DSEA_TRY(reorth_update_f32(ctx, n, ldq, m, Q, rvec, ctx->cvec, -1.0, rvec, ctx->scal + S_BETA2, st,
-                                       fuse_push ? &pp : nullptr));
+                                       fuse_push ? &pp : nullptr, /*defer_norm=*/true));
+            n_beta2 = ctx->pending_norm_n;
+            ctx->pending_norm_n = 0;
         }
-        lanczos_record_kernel<<<1, 1, 0, st>>>(ctx->scal, alpha, beta, i, more ? 1 : 0);
+        lanczos_record_kernel<<<1, (n_alpha > 0 || n_beta2 > 0) ? 256 : 1, 0, st>>>(
+            ctx->scal, alpha, beta, i, more ? 1 : 0, ctx->partials + kDotPartialsOffset, n_alpha, ctx->partials, n_beta2);
         count_launch(ctx);
         DSEA_CUDA(cudaGetLastError());
         if (more) DSEA_TRY(scale_round_store(ctx, n, rvec, ctx->scal + S_INVBETA, qcur, Q + (int64_t)m * ldq, st));
@@ -656,7 +692,7 @@ int dsea_lanczos(dsea_ctx* ctx, const dsea_op* op, const double* param, int k, i
         const bool fs = fuse_scale && i > 0;
         DSEA_TRY(apply_op(ctx, op, param, nullptr, qi, u, ctx->scal + S_ALPHA_L, opwork, st,
                           pre ? XCH_PREPUSHED : XCH_PUSH, ctx->scal + S_INVBETA, fs ? ctx->scal + S_INVBETA : nullptr,
-                          fs ? qi : nullptr));                                     // Lanczos.py:54-55,71-72 (alpha in the epilogue)
+                          fs ? qi : nullptr, false, /*defer_dot=*/true));          // Lanczos.py:54-55,71-72 (alpha in the epilogue)
         DSEA_TRY(lanczos_step_impl(ctx, n, ldq, k, i, Q, u, alpha, beta, st, true, fuse_push, !fuse_scale));
     }
     return lanczos_ritz_impl(ctx, n, ldq, k, which, Q, alpha, beta, evals, evec_min, evec_max, info_host, st);

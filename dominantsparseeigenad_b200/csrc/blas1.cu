@@ -26,8 +26,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
     if (threadIdx.x == 0) out[col] = s;
 }
 
-int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st) {
-    finalize_kernel<<<ncols, 128, 0, st>>>(ctx->partials, nblocks, ncols, out);
+int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st, const double* src) {
+    finalize_kernel<<<ncols, 128, 0, st>>>(src ? src : ctx->partials, nblocks, ncols, out);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;

@@ -68,10 +68,11 @@ __global__ void cg_first_check_kernel(double* scal) {
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
                     const double* __restrict__ Ad, int64_t n, const double* __restrict__ scal,
-                    double* __restrict__ partials) {
+                    double* __restrict__ partials, const double* __restrict__ dad_partials, int n_dad) {
     __shared__ double red[32];
     if (scal[S_DONE] != 0.0) return;
-    const double alpha = scal[S_RR] / scal[S_DAD];
+    const double dad = n_dad > 0 ? sum_partials_seq(dad_partials, n_dad) : scal[S_DAD];   // deferred matvec epilogue
+    const double alpha = scal[S_RR] / dad;
     double s = 0.0;
     const int64_t n2 = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -96,9 +97,19 @@ cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
-// scalar bookkeeping of one iteration (single thread)                             (CG.py:35-38)
-__global__ void cg_scalar_kernel(double* scal) {
+// scalar bookkeeping of one iteration                                              (CG.py:35-38)
+// n_rr > 0: one CTA first sums the |r|^2 partials of the update kernel itself (fixed order), replacing the separate
+// finalize launch; otherwise S_RR_NEW was reduced (and, when sharded, all-reduced) before.
+__global__ void __launch_bounds__(256) cg_scalar_kernel(double* scal, const double* __restrict__ rr_partials, int n_rr) {
+    __shared__ double red[32];
     if (scal[S_DONE] != 0.0) return;
+    if (n_rr > 0) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n_rr; i += blockDim.x) s += rr_partials[i];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) scal[S_RR_NEW] = s;
+    }
+    if (threadIdx.x != 0) return;
     const double rr_new = scal[S_RR_NEW];
     const double it = scal[S_ITERS] + 1.0;
     scal[S_ITERS] = it;
@@ -164,18 +175,24 @@ int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double*
 
 // one iteration AFTER Ad and d.Ad (scal[S_DAD]) are available
 int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st,
-               const PeerPtrs* peers) {
+               const PeerPtrs* peers, int n_dad) {
     const int grid = cg_grid(ctx, n);
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
     int tok = prof_begin(ctx, PK_CG_UPDATE, 48.0 * (double)n, st);
-    cg_update_xr_kernel<<<grid, kCgThreads, 0, st>>>(x, r, d, Ad, n, ctx->scal, ctx->partials);
+    const bool fused = ctx->world == 1 && ctx->fuse_small;
+    cg_update_xr_kernel<<<grid, kCgThreads, 0, st>>>(x, r, d, Ad, n, ctx->scal, ctx->partials,
+                                                     ctx->partials + kDotPartialsOffset, n_dad);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
-    DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
-    cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    if (fused) {
+        cg_scalar_kernel<<<1, 256, 0, st>>>(ctx->scal, ctx->partials, grid);
+    } else {
+        DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
+        cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal, nullptr, 0);
+    }
     prof_guard_next_phase(ctx);
     tok = prof_begin(ctx, PK_CG_UPDATE, (24.0 + 8.0 * pp.n) * (double)n, st);
     cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal, pp);

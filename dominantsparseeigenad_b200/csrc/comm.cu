@@ -179,9 +179,10 @@ static int mail_launch(dsea_ctx* ctx, const double* partials, int nblocks, int n
     return DSEA_OK;
 }
 
-int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st) {
-    if (ctx->world > 1 && ctx->mail_ok && ncols <= kMaxK) return mail_launch(ctx, ctx->partials, nblocks, ncols, out, st);
-    DSEA_TRY(finalize_partials(ctx, nblocks, ncols, out, st));
+int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st, const double* src) {
+    if (!src) src = ctx->partials;
+    if (ctx->world > 1 && ctx->mail_ok && ncols <= kMaxK) return mail_launch(ctx, src, nblocks, ncols, out, st);
+    DSEA_TRY(finalize_partials(ctx, nblocks, ncols, out, st, src));
     return allreduce_sum(ctx, out, ncols, st);
 }
 

@@ -42,6 +42,10 @@ constexpr int kMaxSweeps = 40;      // worst case: one new spin bit per sweep (t
 constexpr int kMaxPartialBlocks = 4096;   // upper bound on CTAs writing reduction partials
 constexpr int kMaxK = 2048;               // max Lanczos vectors
 constexpr int64_t kPartialDoubles = 4 << 20;   // 32 MB of per-CTA partial sums (>= kMaxPartialBlocks * 1024)
+// The last 8192 doubles hold the partial sums of a matvec's dot epilogue.  On one GPU the consumer kernels sum
+// them in their own prologue (fixed sequential order => bit-identical in every thread) instead of waiting for a
+// separate finalize launch; the main region [0, kDotPartialsOffset) stays free for the consumer's own partials.
+constexpr int64_t kDotPartialsOffset = kPartialDoubles - 8192;
 
 // ---- device scalars kept in ctx->scal (all double) -------------------------------------------
 enum ScalarSlot {
@@ -81,6 +85,8 @@ struct Recurrence {
     const double* alpha;
     const double* beta;
     double* r0_out;
+    const double* alpha_partials = nullptr;   // n_alpha > 0: alpha = sum of these (deferred matvec dot epilogue)
+    int n_alpha = 0;
 };
 
 struct NcclApi;   // resolved with dlopen at context creation (comm.cu)
@@ -145,6 +151,9 @@ struct dsea_ctx {
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
     double polish_eps = 1e-10;          // absolute CG tolerance of the Jacobi-Davidson polish (fp32 basis)
     int64_t last_polish_iters = 0;
+    int fuse_small = 1;                 // one GPU: consumers sum matvec / norm partials themselves (no finalize launches)
+    int pending_dot_n = 0;              // > 0: the last matvec left this many dot partials at partials + kDotPartialsOffset
+    int pending_norm_n = 0;             // > 0: the last reorth pass 2 left this many |r|^2 partials at partials
     int basis_fp32 = 0;                 // opt-in: Lanczos basis also kept as an fp32 shadow that the reorth passes stream
 };
 
@@ -180,7 +189,7 @@ enum { XCH_PUSH = 0, XCH_PREPUSHED = 1, XCH_PREPUSHED_BARRIER = 2 };
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
                double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st,
                int exchange = XCH_PUSH, const double* remote_scale = nullptr, const double* in_scale = nullptr,
-               double* q_out = nullptr, bool round_remote = false);
+               double* q_out = nullptr, bool round_remote = false, bool defer_dot = false);
 bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op);
 int tfim_dHdg(dsea_ctx* ctx, const dsea_op* op, const double* v, double* u, double* work, cudaStream_t st);
 int tfim_adjoint(dsea_ctx* ctx, const dsea_op* op, const double* v1, const double* v2, double* out,
@@ -195,9 +204,10 @@ int outer(dsea_ctx* ctx, int64_t n, double scale, const double* a, const double*
 // reorth.cu
 int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u, double* c_out,
                 cudaStream_t st, const Recurrence* rec = nullptr);   // c_out = Q^T (u [- recurrence terms])  (allreduced)
+// `defer_norm`: leave the |r|^2 partials in ctx->partials (ctx->pending_norm_n) for the consumer to sum
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const double* Q, const double* u,
                   const double* c, double sign, double* r_out, double* norm2_out,
-                  cudaStream_t st, const PeerPtrs* peers = nullptr);   // r = u + sign * Q c  (u may be NULL)
+                  cudaStream_t st, const PeerPtrs* peers = nullptr, bool defer_norm = false);   // r = u + sign * Q c  (u may be NULL)
 int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, cudaStream_t st);
 // fp32 shadow basis (opt-in "basis_fp32"): the same two passes over float columns with fp64 accumulation, and the
 // normalisation that rounds the new vector to fp32 (q32 = fl32(r * *scale), q64 = the same values widened)
@@ -205,7 +215,7 @@ int reorth_dots_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const floa
                     cudaStream_t st, const Recurrence* rec = nullptr);
 int reorth_update_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int ncols, const float* Q, const double* u,
                       const double* c, double sign, double* r_out, double* norm2_out, cudaStream_t st,
-                      const PeerPtrs* peers = nullptr);
+                      const PeerPtrs* peers = nullptr, bool defer_norm = false);
 int scale_round_store(dsea_ctx* ctx, int64_t n, const double* r, const double* scale, double* q64, float* q32,
                       cudaStream_t st);
 // blas1.cu
@@ -213,9 +223,10 @@ int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out,
 int axpby(dsea_ctx* ctx, int64_t n, const double* a, const double* x, const double* b, double* y, cudaStream_t st);
 int project(dsea_ctx* ctx, int64_t n, const double* psi, const double* b, double* out, cudaStream_t st);
 int randn(dsea_ctx* ctx, int64_t n, uint64_t seed, uint64_t sid, uint64_t offset, double* out, cudaStream_t st);
-int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st);
+int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st, const double* src = nullptr);
 // second reduction stage + cross-rank sum in one step (fused peer-memory kernel when available)
-int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st);   // comm.cu
+int finalize_reduce(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st,
+                    const double* src = nullptr);   // comm.cu; src defaults to ctx->partials
 // tridiag.cu
 int tridiag_extreme(dsea_ctx* ctx, int k, int which, const double* alpha, const double* beta, const double* keff,
                     double* evals, double* y_min, double* y_max, cudaStream_t st);
@@ -224,8 +235,9 @@ int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st);
 // `peers`: when non-null the kernels that write the search direction d also store it into the partners' arenas
 int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double* r, double* d, cudaStream_t st,
             const PeerPtrs* peers = nullptr);
+// `n_dad` > 0: d.Ad is the sum of that many partials at ctx->partials + kDotPartialsOffset (deferred matvec epilogue)
 int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const double* Ad, cudaStream_t st,
-               const PeerPtrs* peers = nullptr);
+               const PeerPtrs* peers = nullptr, int n_dad = 0);
 // comm.cu
 int comm_init(dsea_ctx* ctx, const void* id);
 int comm_destroy(dsea_ctx* ctx);
@@ -275,6 +287,13 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
         t = warp_sum(t);
     }
     return t;
+}
+
+// Sequential sum of n partials: every thread that calls it obtains the same bits.
+__device__ __forceinline__ double sum_partials_seq(const double* __restrict__ p, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += p[i];
+    return s;
 }
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return *reinterpret_cast<const double2*>(p); }

@@ -89,6 +89,8 @@ struct RecT {
     const double* alpha;
     const double* beta;
     double* r0_out;
+    const double* alpha_partials;
+    int n_alpha;
 };
 
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
@@ -101,7 +103,7 @@ reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restri
     constexpr int kTileRows = kRThreads * 2 * R;
     extern __shared__ double wacc[];                 // [8 warps][m] per-warp accumulators
     // three-term recurrence folded into the prologue: r0 = u - alpha q_i - beta q_{i-1}  (Lanczos.py:61)
-    const double ra = rec.qi ? *rec.alpha : 0.0;
+    const double ra = rec.qi ? (rec.n_alpha > 0 ? sum_partials_seq(rec.alpha_partials, rec.n_alpha) : *rec.alpha) : 0.0;
     const double rb = rec.qim1 ? *rec.beta : 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int j = threadIdx.x; j < 8 * m; j += kRThreads) wacc[j] = 0.0;
@@ -348,7 +350,11 @@ static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT*
     rc.qi = rc.qim1 = nullptr;
     rc.alpha = rc.beta = nullptr;
     rc.r0_out = nullptr;
+    rc.alpha_partials = nullptr;
+    rc.n_alpha = 0;
     if (rec) {
+        rc.alpha_partials = rec->alpha_partials;
+        rc.n_alpha = rec->n_alpha;
         rc.qi = (const QT*)rec->qi;
         rc.qim1 = (const QT*)rec->qim1;
         rc.alpha = rec->alpha;
@@ -364,7 +370,8 @@ static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT*
 
 template <typename QT>
 static int reorth_update_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT* Q, const double* u, const double* c,
-                           double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
+                           double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers,
+                           bool defer_norm) {
     const int grid = reorth_grid(ctx, n, kRThreads * 2 * QTraits<QT>::R);
     const size_t smem = (size_t)m * sizeof(double);
     const double s = (double)sizeof(QT);
@@ -377,8 +384,10 @@ static int reorth_update_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const Q
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
+    ctx->pending_norm_n = 0;
     if (norm2_out) {
-        DSEA_TRY(finalize_reduce(ctx, grid, 1, norm2_out, st));
+        if (defer_norm && ctx->world == 1 && ctx->fuse_small) ctx->pending_norm_n = grid;
+        else DSEA_TRY(finalize_reduce(ctx, grid, 1, norm2_out, st));
     }
     return DSEA_OK;
 }
@@ -389,8 +398,8 @@ int reorth_dots(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, c
 }
 
 int reorth_update(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const double* Q, const double* u, const double* c,
-                  double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
-    return reorth_update_t<double>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers);
+                  double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers, bool defer_norm) {
+    return reorth_update_t<double>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers, defer_norm);
 }
 
 int reorth_dots_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float* Q, const double* u, double* c_out,
@@ -399,8 +408,9 @@ int reorth_dots_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float* Q
 }
 
 int reorth_update_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float* Q, const double* u, const double* c,
-                      double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers) {
-    return reorth_update_t<float>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers);
+                      double sign, double* r_out, double* norm2_out, cudaStream_t st, const PeerPtrs* peers,
+                      bool defer_norm) {
+    return reorth_update_t<float>(ctx, n, ldq, m, Q, u, c, sign, r_out, norm2_out, st, peers, defer_norm);
 }
 
 // ---- K3 for the fp32 shadow basis: q = fl32(r * s) stored twice ---------------------------------------------------

@@ -542,7 +542,7 @@ bool tfim_can_fuse_scale(const dsea_ctx* ctx, const dsea_op* op) {
 static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const double* g, const double* shift,
                     const double* v, double* u, const double* w, double* dot_out, double* work, cudaStream_t st,
                     int exchange, const double* remote_scale, const double* in_scale, double* q_out,
-                    bool round_remote = false) {
+                    bool round_remote = false, bool defer_dot = false) {
     Sweep sw[kMaxSweeps];
     const int L = op->L;
     const int Tmax = clamp_tile_bits(ctx->tfim_tile_bits);
@@ -625,12 +625,12 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
         if (mode_adj) {
             p.w = w;
-            p.partials = ctx->partials + total_partials;   // every sweep contributes partial sums
+            p.partials = ctx->partials + kDotPartialsOffset + total_partials;   // every sweep contributes partial sums
             total_partials += grid;
             DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, pipe, st));
         } else {
             p.w = (last && want_dot) ? w : nullptr;
-            p.partials = (last && want_dot) ? ctx->partials : nullptr;
+            p.partials = (last && want_dot) ? ctx->partials + kDotPartialsOffset : nullptr;
             if (last && want_dot) total_partials = grid;
             if (j == 0) DSEA_TRY(launch_sweep<MODE_FIRST>(ctx, p, grid, pipe, st));
             else DSEA_TRY(launch_sweep<MODE_ACCUM>(ctx, p, grid, pipe, st));
@@ -638,18 +638,23 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
     }
     prof_end(ctx, tok, st);
     if (p2p) ctx->fresh_collective = false;    // the arena was just read: the next push needs a collective first
+    ctx->pending_dot_n = 0;
     if (want_dot) {
-        DSEA_TRY(finalize_reduce(ctx, total_partials, 1, dot_out, st));
+        if (defer_dot && !mode_adj && ctx->world == 1 && ctx->fuse_small) {
+            ctx->pending_dot_n = total_partials;      // the consumer kernel sums them in its prologue
+        } else {
+            DSEA_TRY(finalize_reduce(ctx, total_partials, 1, dot_out, st, ctx->partials + kDotPartialsOffset));
+        }
     }
     return DSEA_OK;
 }
 
 int tfim_apply(dsea_ctx* ctx, const dsea_op* op, const double* g, const double* shift, const double* v,
                double* u, const double* dotw, double* dot_out, double* work, cudaStream_t st, int exchange,
-               const double* remote_scale, const double* in_scale, double* q_out, bool round_remote) {
+               const double* remote_scale, const double* in_scale, double* q_out, bool round_remote, bool defer_dot) {
     // with a fused input scale the dot partner is the SCALED input, which the kernel holds in registers (w == v)
     return tfim_run(ctx, op, false, g, shift, v, u, dotw ? dotw : v, dot_out, work, st, exchange, remote_scale,
-                    in_scale, q_out, round_remote);
+                    in_scale, q_out, round_remote, defer_dot);
 }
 
 // u = (dH/dg) v: the same sweeps with g = 1 and the diagonal dropped (g == nullptr selects this).

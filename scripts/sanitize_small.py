@@ -45,6 +45,21 @@ def main():
     assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
     adj = m2.Hadjoint_to_gadjoint(torch.from_numpy(w).to(dev), torch.from_numpy(v).to(dev)).item()
     assert rel(adj, o.Hadjoint_to_gadjoint(torch.from_numpy(w), torch.from_numpy(v)).item()) < 1e-11
+    # round 2: fused normalisation in the pipelined first sweep (Lanczos at N=15), the fp32 shadow basis with its
+    # Jacobi-Davidson polish (projected CG), and a plan with a DIRECT bit (L = 23: 13 + 9 shared-memory bits + 1)
+    m2.g = torch.tensor([1.25], dtype=torch.float64, device=dev, requires_grad=True)
+    dsea.symeig.setDominantSparseSymeig(m2.H, m2.Hadjoint_to_gadjoint)
+    E15, psi15 = dsea.symeig.DominantSparseSymeig.apply(m2.g, 160, m2.dim, dev)
+    dE15, = torch.autograd.grad(E15, m2.g)
+    dsea.runtime.set_basis_precision("fp32")
+    m2.g = torch.tensor([1.25], dtype=torch.float64, device=dev, requires_grad=True)
+    E15f, psi15f = dsea.symeig.DominantSparseSymeig.apply(m2.g, 160, m2.dim, dev)
+    dsea.runtime.set_basis_precision("fp64")
+    a15 = orc.tfim_analytic(15, 1.25)
+    assert rel(E15f.item(), a15[0]) < 1e-10 and rel(E15.item(), a15[0]) < 1e-10 and rel(dE15.item(), a15[1]) < 1e-6
+    from dominantsparseeigenad_b200 import selfcheck
+    ident = selfcheck.operator_identities(dsea.TFIM(23))
+    assert selfcheck.verdict(ident), ident
     # dense (odd n: ragged reorth tiles) forward + backward
     torch.manual_seed(0)
     n = 333
