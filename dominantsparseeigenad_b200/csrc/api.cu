@@ -101,6 +101,7 @@ static int apply_op(dsea_ctx* ctx, const dsea_op* op, const double* param, const
 
 // ---- Lanczos bookkeeping (single thread) -------------------------------------------------------
 __global__ void lanczos_reset_kernel(double* scal) {
+    pdl_prologue();
     scal[S_KEFF] = 0.0;
     scal[S_BREAK] = 0.0;
 }
@@ -112,6 +113,7 @@ __global__ void lanczos_reset_kernel(double* scal) {
 __global__ void __launch_bounds__(256)
 lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_beta, const double* __restrict__ alpha_partials,
                       int n_alpha, const double* __restrict__ beta2_partials, int n_beta2) {
+    pdl_prologue();
     __shared__ double red[32];
     if (n_beta2 > 0) {
         double s = 0.0;
@@ -139,7 +141,7 @@ lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_
 }
 
 static int lanczos_start_impl(dsea_ctx* ctx, int64_t n, double* Q, cudaStream_t st) {
-    lanczos_reset_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    launch_k(ctx, lanczos_reset_kernel, dim3(1), dim3(1), 0, st, ctx->scal);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     DSEA_TRY(dot(ctx, n, Q, Q, ctx->scal + S_BETA2, st));
@@ -184,7 +186,7 @@ static int lanczos_step_impl(dsea_ctx* ctx, int64_t n, int64_t ldq, int k, int i
         n_beta2 = ctx->pending_norm_n;
         ctx->pending_norm_n = 0;
     }
-    lanczos_record_kernel<<<1, (n_alpha > 0 || n_beta2 > 0) ? 256 : 1, 0, st>>>(
+    launch_k(ctx, lanczos_record_kernel, dim3(1), dim3((n_alpha > 0 || n_beta2 > 0) ? 256 : 1), 0, st, 
         ctx->scal, alpha, beta, i, more ? 1 : 0, ctx->partials + kDotPartialsOffset, n_alpha, ctx->partials, n_beta2);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -216,6 +218,7 @@ static inline int64_t col_stride(int64_t n) { return (n + 15) & ~(int64_t)15; }
 
 // ---- Arnoldi bookkeeping (single thread): H[0..i, i] = c1 + c2, H[i+1, i] = |r| -----------------
 __global__ void arnoldi_record_kernel(double* scal, const double* c1, const double* c2, double* hcol, int i) {
+    pdl_prologue();
     for (int j = 0; j <= i; ++j) hcol[j] = c1[j] + c2[j];
     const double b2 = scal[S_BETA2];
     const double b = b2 > 0.0 ? sqrt(b2) : 0.0;
@@ -549,6 +552,7 @@ int64_t dsea_lanczos_basis_doubles(const dsea_op* op, int k) {
 }
 
 __global__ void polish_scalars_kernel(double* scal) {
+    pdl_prologue();
     // S_TMP0 = 1 / |x| from S_BETA2 = x.x
     const double nn = scal[S_BETA2];
     scal[S_TMP0] = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
@@ -556,6 +560,7 @@ __global__ void polish_scalars_kernel(double* scal) {
 
 __global__ void rayleigh_residual_kernel(const double* __restrict__ x, const double* __restrict__ Ax,
                                          const double* __restrict__ theta, double* __restrict__ b, int64_t n) {
+    pdl_prologue();
     // b = theta x - A x   (right-hand side of the correction equation, orthogonal to x by construction)
     const double th = *theta;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -582,7 +587,7 @@ static int lanczos_polish(dsea_ctx* ctx, const dsea_op* op, const double* param,
         DSEA_TRY(scale_by_inv_sqrt(ctx, n, x, ctx->scal + S_BETA2, st));
         DSEA_TRY(apply_op(ctx, op, param, nullptr, x, Ax, theta_out, cgwork + 3 * ld, st));      // theta = x . A x
         if (pass == 1) break;
-        rayleigh_residual_kernel<<<grid, 256, 0, st>>>(x, Ax, theta_out, b, n);
+        launch_k(ctx, rayleigh_residual_kernel, dim3(grid), dim3(256), 0, st, x, Ax, theta_out, b, n);
         count_launch(ctx);
         DSEA_CUDA(cudaGetLastError());
         DSEA_CUDA(cudaMemsetAsync(delta, 0, (size_t)n * sizeof(double), st));
@@ -613,11 +618,11 @@ static int lanczos_fp32_impl(dsea_ctx* ctx, const dsea_op* op, const double* par
     double* opwork = work + 9 * ld;
     // q0 arrives as n doubles at the start of the basis buffer, which column 0 (n floats) overlaps: move it out first
     DSEA_CUDA(cudaMemcpyAsync(rvec, Qraw, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    lanczos_reset_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    launch_k(ctx, lanczos_reset_kernel, dim3(1), dim3(1), 0, st, ctx->scal);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     DSEA_TRY(dot(ctx, n, rvec, rvec, ctx->scal + S_BETA2, st));
-    polish_scalars_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    launch_k(ctx, polish_scalars_kernel, dim3(1), dim3(1), 0, st, ctx->scal);
     count_launch(ctx);
     DSEA_TRY(scale_round_store(ctx, n, rvec, ctx->scal + S_TMP0, qcur, Q, st));               // Lanczos.py:53
     const bool fuse_push = ctx->p2p_ok && ctx->arena_stride >= n;
@@ -647,7 +652,7 @@ static int lanczos_fp32_impl(dsea_ctx* ctx, const dsea_op* op, const double* par
             n_beta2 = ctx->pending_norm_n;
             ctx->pending_norm_n = 0;
         }
-        lanczos_record_kernel<<<1, (n_alpha > 0 || n_beta2 > 0) ? 256 : 1, 0, st>>>(
+        launch_k(ctx, lanczos_record_kernel, dim3(1), dim3((n_alpha > 0 || n_beta2 > 0) ? 256 : 1), 0, st, 
             ctx->scal, alpha, beta, i, more ? 1 : 0, ctx->partials + kDotPartialsOffset, n_alpha, ctx->partials, n_beta2);
         count_launch(ctx);
         DSEA_CUDA(cudaGetLastError());
@@ -746,7 +751,7 @@ int dsea_arnoldi_step(dsea_ctx* ctx, int64_t n_loc, int m, int i, double* Q, con
     DSEA_TRY(reorth_update(ctx, n_loc, ldq, cols, Q, u, c1, -1.0, qnext, nullptr, st));
     DSEA_TRY(reorth_dots(ctx, n_loc, ldq, cols, Q, qnext, c2, st));
     DSEA_TRY(reorth_update(ctx, n_loc, ldq, cols, Q, qnext, c2, -1.0, qnext, ctx->scal + S_BETA2, st));
-    arnoldi_record_kernel<<<1, 1, 0, st>>>(ctx->scal, c1, c2, H + (int64_t)i * (m + 1), i);
+    launch_k(ctx, arnoldi_record_kernel, dim3(1), dim3(1), 0, st, ctx->scal, c1, c2, H + (int64_t)i * (m + 1), i);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return scale_by_inv_sqrt(ctx, n_loc, qnext, ctx->scal + S_BETA2, st);

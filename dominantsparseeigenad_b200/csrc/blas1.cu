@@ -18,6 +18,7 @@ static inline int stream_grid(const dsea_ctx* ctx, int64_t n, int per_thread = 8
 // ---- second stage of every reduction: out[col] = sum_b partials[b*ncols + col], fixed order ----
 __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict__ partials, int nblocks, int ncols,
                                                        double* __restrict__ out) {
+    pdl_prologue();
     __shared__ double red[32];
     const int col = blockIdx.x;
     double s = 0.0;
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const double* __restrict_
 }
 
 int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaStream_t st, const double* src) {
-    finalize_kernel<<<ncols, 128, 0, st>>>(src ? src : ctx->partials, nblocks, ncols, out);
+    launch_k(ctx, finalize_kernel, dim3(ncols), dim3(128), 0, st, src ? src : ctx->partials, nblocks, ncols, out);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -36,6 +37,7 @@ int finalize_partials(dsea_ctx* ctx, int nblocks, int ncols, double* out, cudaSt
 // ---- dot ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) dot_kernel(const double* __restrict__ a, const double* __restrict__ b,
                                                        int64_t n, double* __restrict__ partials) {
+    pdl_prologue();
     __shared__ double red[32];
     double s = 0.0;
     const int64_t n2 = n >> 1;
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) dot_kernel(const double* __restrict_
 
 int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st) {
     const int grid = stream_grid(ctx, n);
-    dot_kernel<<<grid, kThreads, 0, st>>>(a, b, n, ctx->partials);
+    launch_k(ctx, dot_kernel, dim3(grid), dim3(kThreads), 0, st, a, b, n, ctx->partials);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return finalize_reduce(ctx, grid, 1, out, st);
@@ -61,6 +63,7 @@ int dot(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out,
 __global__ void __launch_bounds__(kThreads) axpby_kernel(const double* __restrict__ pa, const double* __restrict__ x,
                                                          const double* __restrict__ pb, double* __restrict__ y,
                                                          int64_t n) {
+    pdl_prologue();
     const double a = pa ? *pa : 1.0, b = pb ? *pb : 1.0;
     const int64_t n2 = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kThreads) axpby_kernel(const double* __restric
 }
 
 int axpby(dsea_ctx* ctx, int64_t n, const double* a, const double* x, const double* b, double* y, cudaStream_t st) {
-    axpby_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(a, x, b, y, n);
+    launch_k(ctx, axpby_kernel, dim3(stream_grid(ctx, n)), dim3(kThreads), 0, st, a, x, b, y, n);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(kThreads) project_apply_kernel(const double* _
                                                                  const double* __restrict__ b,
                                                                  const double* __restrict__ pdot,
                                                                  double* __restrict__ out, int64_t n) {
+    pdl_prologue();
     const double d = *pdot;
     const int64_t n2 = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) project_apply_kernel(const double* _
 int project(dsea_ctx* ctx, int64_t n, const double* psi, const double* b, double* out, cudaStream_t st) {
     double* d = ctx->scal + S_TMP0;
     DSEA_TRY(dot(ctx, n, psi, b, d, st));
-    project_apply_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(psi, b, d, out, n);
+    launch_k(ctx, project_apply_kernel, dim3(stream_grid(ctx, n)), dim3(kThreads), 0, st, psi, b, d, out, n);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -108,6 +112,7 @@ int project(dsea_ctx* ctx, int64_t n, const double* psi, const double* b, double
 // ---- x *= 1/sqrt(norm2)  (K3: normalise a new Lanczos vector in place) ----------------------------
 __global__ void __launch_bounds__(kThreads) scale_inv_sqrt_kernel(double* __restrict__ x,
                                                                   const double* __restrict__ norm2, int64_t n) {
+    pdl_prologue();
     const double nn = *norm2;
     const double s = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;     // breakdown (|r| == 0) leaves a zero column
     const int64_t n2 = n >> 1;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) scale_inv_sqrt_kernel(double* __rest
 
 int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, cudaStream_t st) {
     const int tok = prof_begin(ctx, PK_NORMALISE, 16.0 * (double)n, st);
-    scale_inv_sqrt_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(x, norm2, n);
+    launch_k(ctx, scale_inv_sqrt_kernel, dim3(stream_grid(ctx, n)), dim3(kThreads), 0, st, x, norm2, n);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -132,6 +137,7 @@ int scale_by_inv_sqrt(dsea_ctx* ctx, int64_t n, double* x, const double* norm2, 
 
 // ---- publish a shard to the partners' arenas (NVLink stores), used when no producing kernel can ----
 __global__ void __launch_bounds__(kThreads) push_kernel(const double* __restrict__ v, int64_t n, PeerPtrs peers) {
+    pdl_prologue();
     const int64_t n2 = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) push_kernel(const double* __restrict
 }
 
 int push_to_peers(dsea_ctx* ctx, const double* v, int64_t n, cudaStream_t st) {
-    push_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(v, n, peer_ptrs(ctx));
+    launch_k(ctx, push_kernel, dim3(stream_grid(ctx, n)), dim3(kThreads), 0, st, v, n, peer_ptrs(ctx));
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -163,6 +169,7 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 
 __global__ void __launch_bounds__(kThreads) randn_kernel(double* __restrict__ out, int64_t n, uint64_t seed,
                                                          uint64_t sid, uint64_t offset) {
+    pdl_prologue();
     const int64_t n2 = (n + 1) >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) randn_kernel(double* __restrict__ ou
 }
 
 int randn(dsea_ctx* ctx, int64_t n, uint64_t seed, uint64_t sid, uint64_t offset, double* out, cudaStream_t st) {
-    randn_kernel<<<stream_grid(ctx, n, 4), kThreads, 0, st>>>(out, n, seed, sid, offset);
+    launch_k(ctx, randn_kernel, dim3(stream_grid(ctx, n, 4)), dim3(kThreads), 0, st, out, n, seed, sid, offset);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;

@@ -21,6 +21,7 @@ static inline int cg_grid(const dsea_ctx* ctx, int64_t n) {
 }
 
 __global__ void cg_setup_kernel(double* scal, double eps, double maxit) {
+    pdl_prologue();
     scal[S_DONE] = 0.0;
     scal[S_ITERS] = 0.0;
     scal[S_EPS] = eps;
@@ -34,6 +35,7 @@ __global__ void cg_setup_kernel(double* scal, double eps, double maxit) {
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(const double* __restrict__ b, const double* __restrict__ Ax, double* __restrict__ r,
                double* __restrict__ d, int64_t n, double* __restrict__ partials, const PeerPtrs peers) {
+    pdl_prologue();
     __shared__ double red[32];
     double s = 0.0;
     const int64_t n2 = n >> 1;
@@ -59,6 +61,7 @@ cg_init_kernel(const double* __restrict__ b, const double* __restrict__ Ax, doub
 
 // after the initial residual: |r0| < eps  =>  done (CG.py:28-29)
 __global__ void cg_first_check_kernel(double* scal) {
+    pdl_prologue();
     const double rn = sqrt(scal[S_RR]);
     scal[S_RNORM] = rn;
     if (rn < scal[S_EPS]) scal[S_DONE] = 1.0;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
                     const double* __restrict__ Ad, int64_t n, const double* __restrict__ scal,
                     double* __restrict__ partials, const double* __restrict__ dad_partials, int n_dad) {
+    pdl_prologue();
     __shared__ double red[32];
     if (scal[S_DONE] != 0.0) return;
     const double dad = n_dad > 0 ? sum_partials_seq(dad_partials, n_dad) : scal[S_DAD];   // deferred matvec epilogue
@@ -101,6 +105,7 @@ cg_update_xr_kernel(double* __restrict__ x, double* __restrict__ r, const double
 // n_rr > 0: one CTA first sums the |r|^2 partials of the update kernel itself (fixed order), replacing the separate
 // finalize launch; otherwise S_RR_NEW was reduced (and, when sharded, all-reduced) before.
 __global__ void __launch_bounds__(256) cg_scalar_kernel(double* scal, const double* __restrict__ rr_partials, int n_rr) {
+    pdl_prologue();
     __shared__ double red[32];
     if (scal[S_DONE] != 0.0) return;
     if (n_rr > 0) {
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(256) cg_scalar_kernel(double* scal, const doub
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_d_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t n, const double* __restrict__ scal,
                    const PeerPtrs peers) {
+    pdl_prologue();
     if (scal[S_DONE] != 0.0) return;
     const double beta = scal[S_BETA];
     const int64_t n2 = n >> 1;
@@ -151,7 +157,7 @@ cg_update_d_kernel(double* __restrict__ d, const double* __restrict__ r, int64_t
 }
 
 int cg_setup(dsea_ctx* ctx, double eps, int64_t maxit, cudaStream_t st) {
-    cg_setup_kernel<<<1, 1, 0, st>>>(ctx->scal, eps, (double)maxit);
+    launch_k(ctx, cg_setup_kernel, dim3(1), dim3(1), 0, st, ctx->scal, eps, (double)maxit);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -163,11 +169,11 @@ int cg_init(dsea_ctx* ctx, int64_t n, const double* b, const double* Ax, double*
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
-    cg_init_kernel<<<grid, kCgThreads, 0, st>>>(b, Ax, r, d, n, ctx->partials, pp);
+    launch_k(ctx, cg_init_kernel, dim3(grid), dim3(kCgThreads), 0, st, b, Ax, r, d, n, ctx->partials, pp);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR, st));
-    cg_first_check_kernel<<<1, 1, 0, st>>>(ctx->scal);
+    launch_k(ctx, cg_first_check_kernel, dim3(1), dim3(1), 0, st, ctx->scal);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -182,20 +188,20 @@ int cg_iterate(dsea_ctx* ctx, int64_t n, double* x, double* r, double* d, const 
     if (peers) pp = *peers;
     int tok = prof_begin(ctx, PK_CG_UPDATE, 48.0 * (double)n, st);
     const bool fused = ctx->world == 1 && ctx->fuse_small;
-    cg_update_xr_kernel<<<grid, kCgThreads, 0, st>>>(x, r, d, Ad, n, ctx->scal, ctx->partials,
+    launch_k(ctx, cg_update_xr_kernel, dim3(grid), dim3(kCgThreads), 0, st, x, r, d, Ad, n, ctx->scal, ctx->partials,
                                                      ctx->partials + kDotPartialsOffset, n_dad);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (fused) {
-        cg_scalar_kernel<<<1, 256, 0, st>>>(ctx->scal, ctx->partials, grid);
+        launch_k(ctx, cg_scalar_kernel, dim3(1), dim3(256), 0, st, ctx->scal, ctx->partials, grid);
     } else {
         DSEA_TRY(finalize_reduce(ctx, grid, 1, ctx->scal + S_RR_NEW, st));
-        cg_scalar_kernel<<<1, 1, 0, st>>>(ctx->scal, nullptr, 0);
+        launch_k(ctx, cg_scalar_kernel, dim3(1), dim3(1), 0, st, ctx->scal, nullptr, 0);
     }
     prof_guard_next_phase(ctx);
     tok = prof_begin(ctx, PK_CG_UPDATE, (24.0 + 8.0 * pp.n) * (double)n, st);
-    cg_update_d_kernel<<<grid, kCgThreads, 0, st>>>(d, r, n, ctx->scal, pp);
+    launch_k(ctx, cg_update_d_kernel, dim3(grid), dim3(kCgThreads), 0, st, d, r, n, ctx->scal, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx, 2);
     DSEA_CUDA(cudaGetLastError());

@@ -135,6 +135,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __global__ void __launch_bounds__(128)
 finalize_allreduce_kernel(const double* __restrict__ partials, int nblocks, int ncols, double* __restrict__ out,
                           const MailParams mp) {
+    pdl_prologue();
     __shared__ double red[32];
     __shared__ double vals[kMaxMailRanks];
     const int col = blockIdx.x;
@@ -172,7 +173,7 @@ static int mail_launch(dsea_ctx* ctx, const double* partials, int nblocks, int n
     mp.world = ctx->world;
     mp.rank = ctx->rank;
     mp.seq = ++ctx->mail_seq;
-    finalize_allreduce_kernel<<<ncols, 128, 0, st>>>(partials, nblocks, ncols, out, mp);
+    launch_k(ctx, finalize_allreduce_kernel, dim3(ncols), dim3(128), 0, st, partials, nblocks, ncols, out, mp);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     ctx->fresh_collective = true;

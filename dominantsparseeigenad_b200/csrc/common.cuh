@@ -151,6 +151,7 @@ struct dsea_ctx {
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
     double polish_eps = 1e-10;          // absolute CG tolerance of the Jacobi-Davidson polish (fp32 basis)
     int64_t last_polish_iters = 0;
+    int pdl = 1;                        // programmatic dependent launch for every kernel of the library
     int fuse_small = 1;                 // one GPU: consumers sum matvec / norm partials themselves (no finalize launches)
     int pending_dot_n = 0;              // > 0: the last matvec left this many dot partials at partials + kDotPartialsOffset
     int pending_norm_n = 0;             // > 0: the last reorth pass 2 left this many |r|^2 partials at partials
@@ -258,6 +259,30 @@ inline PeerPtrs peer_ptrs(const dsea_ctx* ctx) {
 
 inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
 
+#ifdef __CUDACC__
+// Every kernel of the library is launched through launch_k: with "pdl" on (default) the launch carries the
+// programmatic-stream-serialization attribute, so its CTAs may be scheduled while the previous kernel of the stream is
+// still draining; each kernel starts with pdl_prologue() = griddepcontrol.launch_dependents (let MY successor be
+// scheduled early too) + griddepcontrol.wait (block until the predecessor grid has completed and its writes are
+// visible) BEFORE its first global-memory access.  That hides the 2-3 us launch latency between the ~2500 dependent
+// kernels of a solve without changing any ordering.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(const dsea_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (ctx && ctx->pdl) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Per-kernel timing with CUDA events on the launching stream (no-ops unless dsea_profile_enable()).
 int prof_begin(dsea_ctx* ctx, int kind, double algorithmic_bytes, cudaStream_t st);
 void prof_end(dsea_ctx* ctx, int token, cudaStream_t st);
@@ -289,10 +314,18 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
-// Sequential sum of n partials: every thread that calls it obtains the same bits.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Sum of n partials computed redundantly by every (full) warp with a fixed lane-strided + xor-shuffle order: every
+// thread of every CTA that calls it obtains the same bits.  Must be called by all 32 lanes of the warp.
 __device__ __forceinline__ double sum_partials_seq(const double* __restrict__ p, int n) {
     double s = 0.0;
-    for (int i = 0; i < n; ++i) s += p[i];
+    for (int i = threadIdx.x & 31; i < n; i += 32) s += p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
 

@@ -98,6 +98,7 @@ template <typename QT>
 __global__ void __launch_bounds__(kRThreads, 2)
 reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restrict__ u, int64_t n, int m,
                    double* __restrict__ partials, const RecT<QT> rec) {
+    pdl_prologue();
     typedef QTraits<QT> TR;
     constexpr int R = TR::R;
     constexpr int kTileRows = kRThreads * 2 * R;
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kRThreads, 2)
 reorth_update_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restrict__ u,
                      const double* __restrict__ c, double sign, int64_t n, int m, double* __restrict__ r,
                      double* __restrict__ partials, const PeerPtrs peers) {
+    pdl_prologue();
     typedef QTraits<QT> TR;
     constexpr int R = TR::R;
     constexpr int kTileRows = kRThreads * 2 * R;
@@ -361,7 +363,7 @@ static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT*
         rc.beta = rec->beta;
         rc.r0_out = rec->r0_out;
     }
-    reorth_dots_kernel<QT><<<grid, kRThreads, smem, st>>>(Q, ldq, u, n, m, ctx->partials, rc);
+    launch_k(ctx, reorth_dots_kernel<QT>, dim3(grid), dim3(kRThreads), smem, st, Q, ldq, u, n, m, ctx->partials, rc);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
@@ -379,7 +381,7 @@ static int reorth_update_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const Q
     PeerPtrs pp;
     pp.n = 0;
     if (peers) pp = *peers;
-    reorth_update_kernel<QT><<<grid, kRThreads, smem, st>>>(Q, ldq, u, c, sign, n, m, r_out,
+    launch_k(ctx, reorth_update_kernel<QT>, dim3(grid), dim3(kRThreads), smem, st, Q, ldq, u, c, sign, n, m, r_out,
                                                            norm2_out ? ctx->partials : nullptr, pp);
     prof_end(ctx, tok, st);
     count_launch(ctx);
@@ -417,6 +419,7 @@ int reorth_update_f32(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const float*
 // q32 receives the rounded vector (the basis column), q64 the same values widened (the next matvec's input).
 __global__ void __launch_bounds__(256) scale_round_kernel(const double* __restrict__ r, const double* __restrict__ ps,
                                                           double* __restrict__ q64, float* __restrict__ q32, int64_t n) {
+    pdl_prologue();
     const double s = *ps;
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -444,7 +447,7 @@ int scale_round_store(dsea_ctx* ctx, int64_t n, const double* r, const double* s
     if (want < 1) want = 1;
     const int grid = (int)(want < cap ? want : cap);
     const int tok = prof_begin(ctx, PK_NORMALISE, 20.0 * (double)n, st);
-    scale_round_kernel<<<grid, 256, 0, st>>>(r, scale, q64, q32, n);
+    launch_k(ctx, scale_round_kernel, dim3(grid), dim3(256), 0, st, r, scale, q64, q32, n);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());

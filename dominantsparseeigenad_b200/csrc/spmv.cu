@@ -13,6 +13,7 @@ csr_row_per_thread_kernel(int64_t n, const int64_t* __restrict__ rowptr, const i
                           const double* __restrict__ vals, const double* __restrict__ pdiag,
                           const double* __restrict__ shift, const double* __restrict__ v, double* __restrict__ u,
                           double* __restrict__ partials, const double* __restrict__ guard) {
+    pdl_prologue();
     __shared__ double red[32];
     if (guard && *guard != 0.0) return;
     const double sh = shift ? *shift : 0.0;
@@ -39,6 +40,7 @@ csr_row_per_warp_kernel(int64_t n, const int64_t* __restrict__ rowptr, const int
                         const double* __restrict__ vals, const double* __restrict__ pdiag,
                         const double* __restrict__ shift, const double* __restrict__ v, double* __restrict__ u,
                         double* __restrict__ partials, const double* __restrict__ guard) {
+    pdl_prologue();
     __shared__ double red[32];
     if (guard && *guard != 0.0) return;
     const double sh = shift ? *shift : 0.0;
@@ -73,12 +75,12 @@ int csr_apply(dsea_ctx* ctx, const dsea_op* op, const double* pdiag, const doubl
     if (avg <= 12.0) {
         int64_t want = (n + 255) / 256;
         grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-        csr_row_per_thread_kernel<<<grid, 256, 0, st>>>(n, op->rowptr, op->colidx, op->vals, pdiag, shift, v, u,
+        launch_k(ctx, csr_row_per_thread_kernel, dim3(grid), dim3(256), 0, st, n, op->rowptr, op->colidx, op->vals, pdiag, shift, v, u,
                                                         dot_out ? ctx->partials : nullptr, ctx->guard);
     } else {
         int64_t want = (n + 7) / 8;
         grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-        csr_row_per_warp_kernel<<<grid, 256, 0, st>>>(n, op->rowptr, op->colidx, op->vals, pdiag, shift, v, u,
+        launch_k(ctx, csr_row_per_warp_kernel, dim3(grid), dim3(256), 0, st, n, op->rowptr, op->colidx, op->vals, pdiag, shift, v, u,
                                                       dot_out ? ctx->partials : nullptr, ctx->guard);
     }
     count_launch(ctx);
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256)
 dense_gemv_kernel(int64_t n, int64_t ld, const double* __restrict__ A, const double* __restrict__ shift,
                   const double* __restrict__ v, double* __restrict__ u, double* __restrict__ partials,
                   const double* __restrict__ guard) {
+    pdl_prologue();
     __shared__ double red[32];
     if (guard && *guard != 0.0) return;
     const double sh = shift ? *shift : 0.0;
@@ -130,7 +133,7 @@ int dense_apply(dsea_ctx* ctx, const dsea_op* op, const double* shift, const dou
     int64_t want = (n + 7) / 8;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-    dense_gemv_kernel<<<grid, 256, 0, st>>>(n, op->ld, op->A, shift, v, u, dot_out ? ctx->partials : nullptr, ctx->guard);
+    launch_k(ctx, dense_gemv_kernel, dim3(grid), dim3(256), 0, st, n, op->ld, op->A, shift, v, u, dot_out ? ctx->partials : nullptr, ctx->guard);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     if (dot_out) DSEA_TRY(finalize_partials(ctx, grid, 1, dot_out, st));
@@ -140,6 +143,7 @@ int dense_apply(dsea_ctx* ctx, const dsea_op* op, const double* shift, const dou
 // ---- adjoints for explicit matrices ------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hadamard_kernel(int64_t n, const double* __restrict__ a,
                                                        const double* __restrict__ b, double* __restrict__ out) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] * b[i];
 }
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(256) hadamard_kernel(int64_t n, const double* 
 int hadamard(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double* out, cudaStream_t st) {
     int64_t want = (n + 255) / 256;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
-    hadamard_kernel<<<(int)(want < cap ? (want < 1 ? 1 : want) : cap), 256, 0, st>>>(n, a, b, out);
+    launch_k(ctx, hadamard_kernel, dim3((int)(want < cap ? (want < 1 ? 1 : want) : cap)), dim3(256), 0, st, n, a, b, out);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -155,6 +159,7 @@ int hadamard(dsea_ctx* ctx, int64_t n, const double* a, const double* b, double*
 
 __global__ void __launch_bounds__(256) outer_kernel(int64_t n, double scale, const double* __restrict__ a,
                                                     const double* __restrict__ b, double* __restrict__ out) {
+    pdl_prologue();
     const int64_t total = n * n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(256) outer_kernel(int64_t n, double scale, con
 int outer(dsea_ctx* ctx, int64_t n, double scale, const double* a, const double* b, double* out, cudaStream_t st) {
     int64_t want = (n * n + 255) / 256;
     const int64_t cap = (int64_t)ctx->num_sms * 8;
-    outer_kernel<<<(int)(want < cap ? (want < 1 ? 1 : want) : cap), 256, 0, st>>>(n, scale, a, b, out);
+    launch_k(ctx, outer_kernel, dim3((int)(want < cap ? (want < 1 ? 1 : want) : cap)), dim3(256), 0, st, n, scale, a, b, out);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;

@@ -94,6 +94,7 @@ enum { MODE_FIRST = 0, MODE_ACCUM = 1, MODE_ADJ = 2 };
 // ---- generic sweep: any tile size / plan; 2 CTAs per SM, one pair per thread at a time ---------------------
 template <int MODE>
 __global__ void __launch_bounds__(kSweepThreads, 2) tfim_sweep_kernel(const SweepParams p) {
+    pdl_prologue();
     extern __shared__ __align__(16) double tile[];
     __shared__ double red[32];
     if (p.guard && *p.guard != 0.0) return;
@@ -232,6 +233,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 // are in flight while the adds of the current one retire.
 template <int MODE, int THREADS, int LB>
 __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const SweepParams p) {
+    pdl_prologue();
     constexpr int T = kPipeT;
     constexpr int PAIRS = (1 << (T - 1)) / THREADS;            // 16 / 8 / 4 pairs per thread (256 / 512 / 1024 threads)
     constexpr int RBITS = (PAIRS == 16) ? 4 : (PAIRS == 8 ? 3 : 2);   // register-resident top tile bits
@@ -486,7 +488,7 @@ static int launch_pipe(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         done = true;
     }
-    tfim_sweep_pipe_kernel<MODE, THREADS, LB><<<grid, THREADS, smem2, st>>>(p);
+    launch_k(ctx, tfim_sweep_pipe_kernel<MODE, THREADS, LB>, dim3(grid), dim3(THREADS), smem2, st, p);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -513,7 +515,7 @@ static int launch_sweep(dsea_ctx* ctx, const SweepParams& p, int grid, bool pipe
                                        (int)(sizeof(double) << 14)));
         attr_done[MODE] = true;
     }
-    tfim_sweep_kernel<MODE><<<grid, kSweepThreads, smem, st>>>(p);
+    launch_k(ctx, tfim_sweep_kernel<MODE>, dim3(grid), dim3(kSweepThreads), smem, st, p);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;

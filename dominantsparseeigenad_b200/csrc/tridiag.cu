@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(kTriThreads)
 tridiag_kernel(int kmax, int which, const double* __restrict__ alpha, const double* __restrict__ beta,
                const double* __restrict__ keff_ptr, double* __restrict__ evals, double* __restrict__ y_min,
                double* __restrict__ y_max, double* __restrict__ work) {
+    pdl_prologue();
     extern __shared__ double sm[];
     __shared__ int cnt_s[kTriThreads];
     __shared__ double bnd_s[2];
@@ -219,7 +220,7 @@ int tridiag_extreme(dsea_ctx* ctx, int k, int which, const double* alpha, const 
         attr = true;
     }
     const int tok = prof_begin(ctx, PK_TRIDIAG, 16.0 * k, st);
-    tridiag_kernel<<<1, kTriThreads, smem, st>>>(k, which, alpha, beta, keff, evals, y_min, y_max, ctx->tri_work);
+    launch_k(ctx, tridiag_kernel, dim3(1), dim3(kTriThreads), smem, st, k, which, alpha, beta, keff, evals, y_min, y_max, ctx->tri_work);
     prof_end(ctx, tok, st);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
