@@ -121,8 +121,9 @@ lanczos_record_kernel(double* scal, double* alpha, double* beta, int i, int has_
         s = block_sum(s, red);
         if (threadIdx.x == 0) scal[S_BETA2] = s;
     }
+    const double a_sum = n_alpha > 0 ? sum_partials_seq(alpha_partials, n_alpha) : 0.0;   // whole warps take part
     if (threadIdx.x != 0) return;
-    if (n_alpha > 0) scal[S_ALPHA_L] = sum_partials_seq(alpha_partials, n_alpha);
+    if (n_alpha > 0) scal[S_ALPHA_L] = a_sum;
     alpha[i] = scal[S_ALPHA_L];
     if (has_beta) {
         const double b2 = scal[S_BETA2];
@@ -248,6 +249,7 @@ int dsea_ctx_create(int device, int rank, int world, const void* nccl_id_host, d
     ctx->rank = rank;
     ctx->world = world;
     while ((1 << ctx->log2world) < world) ++ctx->log2world;
+    ctx->pdl = (world == 1) ? 1 : 0;        // programmatic dependent launch: on for one GPU (validated there), opt-in when sharded
     cudaDeviceProp prop;
     DSEA_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -336,6 +338,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "reorth_ctas_per_sm")) ctx->reorth_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "basis_fp32")) ctx->basis_fp32 = (value != 0);
     else if (!strcmp(key, "fuse_small")) ctx->fuse_small = (value != 0);
+    else if (!strcmp(key, "pdl")) ctx->pdl = (value != 0);
     else if (!strcmp(key, "polish_eps_1e15")) ctx->polish_eps = 1e-15 * (double)(value < 1 ? 1 : value);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);

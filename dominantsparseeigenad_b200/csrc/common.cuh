@@ -151,7 +151,7 @@ struct dsea_ctx {
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
     double polish_eps = 1e-10;          // absolute CG tolerance of the Jacobi-Davidson polish (fp32 basis)
     int64_t last_polish_iters = 0;
-    int pdl = 1;                        // programmatic dependent launch for every kernel of the library
+    int pdl = 0;                        // programmatic dependent launch for every kernel (set to 1 by ctx_create when world == 1)
     int fuse_small = 1;                 // one GPU: consumers sum matvec / norm partials themselves (no finalize launches)
     int pending_dot_n = 0;              // > 0: the last matvec left this many dot partials at partials + kDotPartialsOffset
     int pending_norm_n = 0;             // > 0: the last reorth pass 2 left this many |r|^2 partials at partials
@@ -260,7 +260,7 @@ inline PeerPtrs peer_ptrs(const dsea_ctx* ctx) {
 inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
 
 #ifdef __CUDACC__
-// Every kernel of the library is launched through launch_k: with "pdl" on (default) the launch carries the
+// Every kernel of the library is launched through launch_k: with "pdl" on (default on one GPU) the launch carries the
 // programmatic-stream-serialization attribute, so its CTAs may be scheduled while the previous kernel of the stream is
 // still draining; each kernel starts with pdl_prologue() = griddepcontrol.launch_dependents (let MY successor be
 // scheduled early too) + griddepcontrol.wait (block until the predecessor grid has completed and its writes are
@@ -314,9 +314,15 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// L1 hazard (found the hard way: CG stopped converging with PDL on).  The per-launch L1 invalidation of a
+// programmatically launched grid happens when ITS CTAs are scheduled, i.e. possibly while the predecessor is still
+// running; a line the predecessor's CTAs load afterwards (the scalar block, a partial-sum array) can then survive in
+// that SM's L1 and be served, stale, to this grid after griddepcontrol.wait.  A gpu-scope fence compiles to
+// MEMBAR + CCTL.IVALL, which invalidates the SM's L1 after the wait, restoring the usual launch-boundary semantics.
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    __threadfence();
 }
 
 // Sum of n partials computed redundantly by every (full) warp with a fixed lane-strided + xor-shuffle order: every

@@ -97,7 +97,8 @@ def context() -> Context:
                          ("mailbox", "DSEA_MAILBOX"), ("tfim_tma", "DSEA_TFIM_TMA"), ("basis_fp32", "DSEA_BASIS_FP32"),
                          ("tfim_direct", "DSEA_TFIM_DIRECT"), ("tfim_fuse_scale", "DSEA_TFIM_FUSE_SCALE"),
                          ("cg_fuse_push", "DSEA_CG_FUSE_PUSH"), ("tfim_pipe_threads", "DSEA_TFIM_PIPE_THREADS"),
-                         ("tfim_generic_min_operands", "DSEA_TFIM_GENERIC_MIN_OPERANDS")):
+                         ("tfim_generic_min_operands", "DSEA_TFIM_GENERIC_MIN_OPERANDS"), ("pdl", "DSEA_PDL"),
+                         ("fuse_small", "DSEA_FUSE_SMALL")):
             if os.environ.get(env):
                 _ctx.set_option(key, int(os.environ[env]))
     return _ctx

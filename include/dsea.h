@@ -64,7 +64,8 @@ int dsea_profile_collect(dsea_ctx* ctx, int nkinds, double* ms_host, double* byt
  * instead of TMA bulk copies), "tfim_pipe_threads" (512 | 256: 4 or 5 register-resident tile bits),
  * "tfim_direct" (0: a third sweep instead of direct loads for the top local bits), "tfim_fuse_scale" (0:
  * separate normalisation pass per Lanczos step), "tfim_l2_prefetch", "tfim_pipe_adjoint", "tfim_pipe_remote",
- * "cg_fuse_push" (0: separate push pass per CG iteration when sharded), "basis_fp32" (1: opt-in fp32 shadow
+ * "cg_fuse_push" (0: separate push pass per CG iteration when sharded), "fuse_small" (0: separate finalize launches
+ * instead of consumers summing partials; one GPU), "pdl" (programmatic dependent launch; default 1 on one GPU, 0 sharded), "basis_fp32" (1: opt-in fp32 shadow
  * of the Lanczos basis for the re-orthogonalisation passes), "p2p" (0 disables the peer-memory exchange; set
  * before creating operators), "mailbox" (0: small all-reduces through NCCL instead of the peer-memory mailbox) */
 int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value);
