@@ -930,3 +930,19 @@ def test_example_drivers_run(dsea, capsys):
     sch = _load_example("schrodinger1D")
     hist = sch.fit("csr", N=300, k=300, steps=3, verbose=False)           # config 1 as shipped, native CSR operator
     assert abs(hist[0] - 0.099454537767) < 1e-9 and hist[-1] < 0.02       # 0.0995 -> 0.0168 -> 0.0097
+
+
+@pytest.mark.parametrize("N,k", [(6, 64), (9, 200), (11, 130)])
+def test_fp32_shadow_basis_ragged_tiles(dsea, N, k):
+    """n_loc below / not a multiple of the 2048-row fp32 reorth tile: the scalar tail paths of both passes and of the
+    rounding store, with k up to the full dimension (breakdown handling)."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    g = 1.3
+    ex = tfim_exact(N, g)
+    dsea.runtime.set_basis_precision("fp32")
+    try:
+        E0, dE0, d2E0, psi = _tfim_E0_family(dsea, N, g, min(k, 1 << N))
+    finally:
+        dsea.runtime.set_basis_precision("fp64")
+    assert rel(E0, ex.E0) < EVAL_RTOL and rel(dE0, ex.dE0) < GRAD_RTOL and rel(d2E0, ex.d2E0) < GRAD_RTOL
+    assert abs(psi.norm().item() - 1.0) < 1e-12
