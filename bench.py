@@ -479,6 +479,14 @@ def main():
             line["fp32_shadow_basis"] = {"config": make_config(N, k, "fp32"), "value": m32["ms_total"] / 1e3 / 3,
                                          "unit": UNIT, "steps": 3, "warmup": 2, "kernels": kernel_table(m32),
                                          "analytic_check": check(m32), "cg_iterations_per_solve": m32["cg_iters"]}
+        if world == 1 and mode == "E0_dE0" and not args.spins:
+            # SURVEY 8d "work accounting": the E0-only backward has a zero right-hand side; the reference (and the headline
+            # above) still runs CG from a random start.  With the opt-in zero start it terminates at once.
+            dsea.runtime.cg_start = "zero"
+            mz = measure(N, k, args.basis, 3, 1, with_e2e=False, with_clocks=False, profile=False)
+            dsea.runtime.cg_start = "random"
+            line["zero_start_cg"] = {"value": mz["ms_total"] / 1e3 / 3, "unit": UNIT, "cg_iterations_per_solve": mz["cg_iters"],
+                                     "analytic_check": check(mz), "note": "opt-in (DSEA_CG_START=zero); not the headline"}
         if world > 1:
             from dominantsparseeigenad_b200 import selfcheck
             line["selfcheck"] = selfcheck.run()

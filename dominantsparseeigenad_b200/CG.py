@@ -31,10 +31,18 @@ def CG_torch(A, b, initialx, sparse=False):
 
 
 def _solve_on_subspace(op, param, E0, b, psi):
-    """x0 random, projected off psi (CG.py:58-59,121-122); then CG on (A - E0)."""
+    """x0 random, projected off psi (CG.py:58-59,121-122); then CG on (A - E0).
+
+    `runtime.cg_start = "zero"` (opt-in) starts from x0 = 0 instead.  The solution on the complement of psi is unique,
+    so the result agrees to the CG tolerance, but a zero right-hand side — the backward pass of a loss that depends on
+    E0 only, where the reference still runs ~100 iterations from its random start — then terminates at
+    once.  The default stays the reference's random start so that benchmarks do the reference's work."""
     rt = context()
-    x0 = runtime.start_vector(op.n_loc, "cg")
-    x0 = project(dev_vec(psi, rt.device), x0)
+    if runtime.cg_start == "zero":
+        x0 = torch.zeros(op.n_loc, dtype=torch.float64, device=rt.device)
+    else:
+        x0 = runtime.start_vector(op.n_loc, "cg")
+        x0 = project(dev_vec(psi, rt.device), x0)
     return op.cg(param, E0, b, x0)
 
 

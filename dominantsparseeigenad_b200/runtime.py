@@ -20,6 +20,7 @@ _ctx = None
 _start_vector_hook: Optional[Callable[[int, str], Optional[torch.Tensor]]] = None
 _draw_counter = 0
 _draw_seed = None
+cg_start = os.environ.get("DSEA_CG_START", "random")      # "random" (reference, CG.py:58,121) | "zero" (opt-in)
 stats = {"cg_iters": [], "lanczos_calls": 0, "cg_calls": 0}
 
 

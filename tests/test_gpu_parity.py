@@ -946,3 +946,22 @@ def test_fp32_shadow_basis_ragged_tiles(dsea, N, k):
         dsea.runtime.set_basis_precision("fp64")
     assert rel(E0, ex.E0) < EVAL_RTOL and rel(dE0, ex.dE0) < GRAD_RTOL and rel(d2E0, ex.d2E0) < GRAD_RTOL
     assert abs(psi.norm().item() - 1.0) < 1e-12
+
+
+def test_zero_start_cg_matches_random_start(dsea):
+    """Opt-in x0 = 0 for the subspace solves: same dE0 / d2E0 / chi_F (the solution on psi-perp is unique), and the
+    E0-only backward (zero right-hand side) needs no iteration at all."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    N, k, g = 16, 160, 1.25
+    ex = tfim_exact(N, g)
+    dsea.runtime.cg_start = "zero"
+    try:
+        dsea.runtime.stats["cg_iters"].clear()
+        E0, dE0, d2E0, _ = _tfim_E0_family(dsea, N, g, k)
+        iters = list(dsea.runtime.stats["cg_iters"])
+        chif = _tfim_chif(dsea, N, g, k)
+    finally:
+        dsea.runtime.cg_start = "random"
+    assert iters[0] == 0                                     # first backward: b = 0
+    assert rel(E0, ex.E0) < EVAL_RTOL and rel(dE0, ex.dE0) < GRAD_RTOL and rel(d2E0, ex.d2E0) < GRAD_RTOL
+    assert rel(chif, ex.chiF) < GRAD_RTOL
