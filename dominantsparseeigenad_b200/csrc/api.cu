@@ -345,6 +345,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "tfim_tma")) ctx->tfim_tma = (value != 0);
     else if (!strcmp(key, "tfim_pipe_threads")) ctx->tfim_pipe_threads = (value == 256 || value == 1024) ? (int)value : 512;
     else if (!strcmp(key, "tfim_unroll")) ctx->tfim_unroll = (value != 0);
+    else if (!strcmp(key, "tfim_stage")) ctx->tfim_stage = (value != 0);
     else if (!strcmp(key, "tfim_generic_min_operands")) ctx->tfim_generic_min_operands = (int)value;
     else if (!strcmp(key, "tfim_direct")) ctx->tfim_direct = (value != 0);
     else if (!strcmp(key, "tfim_fuse_scale")) ctx->tfim_fuse_scale = (value != 0);

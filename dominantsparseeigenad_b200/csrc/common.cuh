@@ -139,6 +139,7 @@ struct dsea_ctx {
     int tfim_pipeline = 1;              // persistent double-buffered sweep kernel for full 2^13 tiles
     int tfim_tma = 1;                   // stage contiguous tiles with TMA bulk copies (UBLKCP + mbarrier) instead of LDGSTS
     int tfim_pipe_threads = 512;        // 256 / 512 / 1024 threads: 16 / 8 / 4 pairs per thread (5 / 4 / 3 register-resident tile bits)
+    int tfim_stage = 1;                 // strided sweeps stage their epilogue operands in thread-private shared-memory slots
     int tfim_generic_min_operands = 4;  // last sweep: direct bits + remote bits from which the generic kernel is used
     int tfim_unroll = 1;                // compile-time flip-bit range in the pipelined kernel (fully unrolled LDS loop)
     int tfim_direct = 1;                // top local bits beyond two sweeps by direct (L2-served) loads instead of a third sweep

@@ -431,6 +431,160 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
     }
 }
 
+// ---- staged strided sweep ----------------------------------------------------------------------------------------
+// ncu's source page of the pipelined strided sweep shows 43 % of its samples in `stall_long_sb`: after the flip phase the
+// epilogue waits, round after round, for operands that live in global memory — the partner tiles of the direct bits, the
+// arena slots of the remote bits, and u (or w for the adjoint).  There are no registers to load them early (x and the
+// accumulators of 2^13 elements fill the file).  This kernel gives every thread PRIVATE shared-memory slots instead:
+// the operands of one SUB-TILE (PAIRS / S of the thread's pairs) are fetched with cp.async while the flip phase of that
+// sub-tile runs, then read back by the same thread (no barrier needed), and the slots are refilled for the next
+// sub-tile.  Costs +1 LDS.128 per operand and pair (the flip phase stays well below the HBM time of the sweep).
+template <int MODE, int S, int LB>
+__global__ void __launch_bounds__(512, 1) tfim_sweep_staged_kernel(const SweepParams p) {
+    pdl_prologue();
+    constexpr int T = kPipeT, THREADS = 512, PAIRS = 8, PPS = PAIRS / S, RBITS = 3, RB0 = T - RBITS;
+    extern __shared__ __align__(128) double bufs[];            // 2 tiles of 2^13 doubles + the staging slots
+    __shared__ double red[32];
+    if (p.guard && *p.guard != 0.0) return;
+    double* stage = bufs + 2 * (1 << T);
+    const int c = p.c;
+    const uint32_t cmask = (1u << c) - 1u;
+    const int dpos = p.hshift + T - c;
+    const double g = (MODE == MODE_ADJ || p.g == nullptr) ? 1.0 : *p.g;
+    const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
+    const int bstart = LB > 0 ? LB : (p.b0 > 1 ? p.b0 : 1);
+    const int nops = p.ndirect + p.nrecv + 1;                  // ... + u (ACCUM) or w (ADJ), always last
+    const double* last_op = (MODE == MODE_ACCUM) ? p.uin : p.w;
+    const bool dot_self = (MODE == MODE_ACCUM) && p.w != nullptr && p.w == p.v;
+    double part = 0.0;
+
+    auto eoff = [&](int j) -> uint32_t { return 2u * (threadIdx.x + THREADS * j); };
+    auto gidx = [&](uint64_t base, uint32_t ee) -> uint64_t {
+        return base | (ee & cmask) | ((uint64_t)(ee >> c) << p.hshift);
+    };
+    auto slot = [&](int o, int jj) -> double* { return stage + 2 * ((size_t)(o * PPS + jj) * THREADS + threadIdx.x); };
+    auto issue_stage = [&](uint64_t base, int sub) {
+        for (int o = 0; o < nops; ++o) {
+#pragma unroll
+            for (int jj = 0; jj < PPS; ++jj) {
+                const uint64_t gi = gidx(base, eoff(sub * PPS + jj));
+                const double* src;
+                if (o < p.ndirect) src = p.v + (gi ^ (1ull << (dpos + o)));
+                else if (o < p.ndirect + p.nrecv) src = p.recv + (uint64_t)(o - p.ndirect) * p.recv_stride + gi;
+                else src = last_op + gi;
+                cp_async16(slot(o, jj), src);
+            }
+        }
+        cp_async_commit();
+    };
+    auto prefetch_tile = [&](uint64_t t, double* buf) {
+        const uint64_t base = tile_base(p, t);
+#pragma unroll
+        for (int j = 0; j < PAIRS; ++j) cp_async16(buf + eoff(j), p.v + gidx(base, eoff(j)));
+        cp_async_commit();
+    };
+
+    uint64_t t = blockIdx.x;
+    int st = 0;
+    if (t < p.ntiles) prefetch_tile(t, bufs);
+    for (; t < p.ntiles; t += gridDim.x, st ^= 1) {
+        const double* buf = bufs + ((size_t)st << T);
+        const uint64_t tn = t + gridDim.x;
+        const uint64_t base = tile_base(p, t);
+        const bool more = tn < p.ntiles;
+        issue_stage(base, 0);                                     // group S0 (slots were consumed last iteration)
+        if (more) prefetch_tile(tn, bufs + ((size_t)(st ^ 1) << T));   // group P
+        if (more) cp_async_wait<2>(); else cp_async_wait<1>();    // this tile's data is the oldest group
+        __syncthreads();
+
+        double2 a[PAIRS];
+        {
+            double2 x[PAIRS];
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) x[j] = *reinterpret_cast<const double2*>(buf + eoff(j));
+#pragma unroll
+            for (int j = 0; j < PAIRS; ++j) a[j] = make_double2(0.0, 0.0);       // strided sweeps never own tile bit 0
+#pragma unroll
+            for (int jb = 0; jb < RBITS; ++jb) {
+                if (LB > 0 || RB0 + jb >= p.b0) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) {
+                        a[j].x += x[j ^ (1 << jb)].x;
+                        a[j].y += x[j ^ (1 << jb)].y;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int sub = 0; sub < S; ++sub) {
+            // flips of this sub-tile's pairs from the shared-memory tile (overlaps the staging copies in flight)
+            if (LB > 0) {
+#pragma unroll
+                for (int b = LB; b < RB0; ++b) {
+#pragma unroll
+                    for (int jj = 0; jj < PPS; ++jj) {
+                        const double2 y = *reinterpret_cast<const double2*>(buf + (eoff(sub * PPS + jj) ^ (1u << b)));
+                        a[sub * PPS + jj].x += y.x;
+                        a[sub * PPS + jj].y += y.y;
+                    }
+                }
+            } else {
+                for (int b = bstart; b < RB0; ++b) {
+#pragma unroll
+                    for (int jj = 0; jj < PPS; ++jj) {
+                        const double2 y = *reinterpret_cast<const double2*>(buf + (eoff(sub * PPS + jj) ^ (1u << b)));
+                        a[sub * PPS + jj].x += y.x;
+                        a[sub * PPS + jj].y += y.y;
+                    }
+                }
+            }
+            // the staged operands of this sub-tile have landed (the tile prefetch may still be in flight behind S0)
+            if (sub == 0 && more) cp_async_wait<1>(); else cp_async_wait<0>();
+            for (int o = 0; o < p.ndirect; ++o) {
+#pragma unroll
+                for (int jj = 0; jj < PPS; ++jj) {
+                    const double2 y = *reinterpret_cast<const double2*>(slot(o, jj));
+                    a[sub * PPS + jj].x += y.x;
+                    a[sub * PPS + jj].y += y.y;
+                }
+            }
+            for (int o = p.ndirect; o < p.ndirect + p.nrecv; ++o) {
+#pragma unroll
+                for (int jj = 0; jj < PPS; ++jj) {
+                    const double2 y = *reinterpret_cast<const double2*>(slot(o, jj));
+                    const double t0 = rscale * y.x, t1 = rscale * y.y;
+                    a[sub * PPS + jj].x += p.round_remote ? (double)(float)t0 : t0;
+                    a[sub * PPS + jj].y += p.round_remote ? (double)(float)t1 : t1;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < PPS; ++jj) {
+                const int j = sub * PPS + jj;
+                const double2 z = *reinterpret_cast<const double2*>(slot(nops - 1, jj));   // u, or w for the adjoint
+                if (MODE == MODE_ADJ) {
+                    part -= z.x * a[j].x + z.y * a[j].y;
+                } else {
+                    const double2 o = make_double2(z.x - g * a[j].x, z.y - g * a[j].y);
+                    stg2(p.uout + gidx(base, eoff(j)), o);
+                    if (dot_self) {
+                        const double2 x = *reinterpret_cast<const double2*>(buf + eoff(j));
+                        part += x.x * o.x + x.y * o.y;
+                    } else if (p.w) {
+                        const double2 wv = ldg2(p.w + gidx(base, eoff(j)));
+                        part += wv.x * o.x + wv.y * o.y;
+                    }
+                }
+            }
+            if (sub + 1 < S) issue_stage(base, sub + 1);          // refill the slots this thread just consumed
+        }
+        __syncthreads();          // everyone is done with `buf` before the next prefetch overwrites it
+    }
+    if (p.partials) {
+        const double tot = block_sum(part, red);
+        if (threadIdx.x == 0) p.partials[blockIdx.x] = tot;
+    }
+}
+
 // Sweep schedule for L local bits with tiles of at most Tmax bits.
 //   run_bits > 0 : every strided sweep uses runs of exactly 2^run_bits doubles (tests / tuning), no direct bits;
 //   run_bits = 0 : automatic.  Runs are at least `cmin` bits long (4 = one 128-byte line for production tiles, 2 for
@@ -492,6 +646,33 @@ static int launch_pipe(dsea_ctx* ctx, const SweepParams& p, int grid, cudaStream
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
+}
+
+template <int MODE, int S, int LB>
+static int launch_staged(dsea_ctx* ctx, const SweepParams& p, int grid, int nops, cudaStream_t st) {
+    const size_t smem = (sizeof(double) << kPipeT) * 2 + (size_t)nops * (8 / S) * 512 * 16;
+    static size_t set = 0;
+    if (smem > set) {
+        DSEA_CUDA(cudaFuncSetAttribute(tfim_sweep_staged_kernel<MODE, S, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        set = smem;
+    }
+    launch_k(ctx, tfim_sweep_staged_kernel<MODE, S, LB>, dim3(grid), dim3(512), smem, st, p);
+    count_launch(ctx);
+    DSEA_CUDA(cudaGetLastError());
+    return DSEA_OK;
+}
+
+// Sub-tile count of the staged kernel for `nops` global operands per element (0: does not fit in shared memory).
+static inline int staged_subtiles(int nops) { return nops <= 3 ? 2 : (nops <= 6 ? 4 : 0); }
+
+template <int MODE>
+static int launch_staged_any(dsea_ctx* ctx, const SweepParams& p, int grid, int nops, cudaStream_t st) {
+    const bool lb4 = ctx->tfim_unroll && p.b0 == 4 && p.c == 4;
+    if (staged_subtiles(nops) == 2) {
+        return lb4 ? launch_staged<MODE, 2, 4>(ctx, p, grid, nops, st) : launch_staged<MODE, 2, 0>(ctx, p, grid, nops, st);
+    }
+    return lb4 ? launch_staged<MODE, 4, 4>(ctx, p, grid, nops, st) : launch_staged<MODE, 4, 0>(ctx, p, grid, nops, st);
 }
 
 template <int MODE, int THREADS>
@@ -622,19 +803,25 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         const bool pipe = pipe_eligible(ctx, sw[j], p.ntiles) && !(mode_adj && !ctx->tfim_pipe_adjoint) &&
                           !(p.nrecv > 0 && !ctx->tfim_pipe_remote) &&
                           !(!mode_adj && p.ndirect + p.nrecv >= ctx->tfim_generic_min_operands);
-        int grid = pipe ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
-                        : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
+        // strided sweeps with global operands in their epilogue take the staged kernel when the slots fit
+        const int nops = p.ndirect + p.nrecv + 1;
+        const bool staged = ctx->tfim_stage && pipe_eligible(ctx, sw[j], p.ntiles) && j > 0 && sw[j].c < sw[j].T &&
+                            sw[j].c >= 1 && staged_subtiles(nops) > 0 && !(mode_adj && !ctx->tfim_pipe_adjoint);
+        int grid = (pipe || staged) ? (int)(p.ntiles < (uint64_t)ctx->num_sms ? p.ntiles : (uint64_t)ctx->num_sms)
+                                    : (int)(p.ntiles < 2048 ? p.ntiles : 2048);
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
         if (mode_adj) {
             p.w = w;
             p.partials = ctx->partials + kDotPartialsOffset + total_partials;   // every sweep contributes partial sums
             total_partials += grid;
-            DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, pipe, st));
+            if (staged) DSEA_TRY(launch_staged_any<MODE_ADJ>(ctx, p, grid, nops, st));
+            else DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, pipe, st));
         } else {
             p.w = (last && want_dot) ? w : nullptr;
             p.partials = (last && want_dot) ? ctx->partials + kDotPartialsOffset : nullptr;
             if (last && want_dot) total_partials = grid;
             if (j == 0) DSEA_TRY(launch_sweep<MODE_FIRST>(ctx, p, grid, pipe, st));
+            else if (staged) DSEA_TRY(launch_staged_any<MODE_ACCUM>(ctx, p, grid, nops, st));
             else DSEA_TRY(launch_sweep<MODE_ACCUM>(ctx, p, grid, pipe, st));
         }
     }

@@ -11,6 +11,7 @@ Variants (dsea_ctx_set_option knobs):
   r1_plan      round 1's plan: 32-byte runs (run_bits = 2), no direct bits, 512 threads
   sweeps3      128-byte runs, no direct bits (a third sweep for the top bits)
   direct       128-byte runs, top local bits by direct (L2-served) loads                  <- default build
+  staged       ... strided sweep with its epilogue operands staged through thread-private shared-memory slots   <- default build
   direct_allpipe / direct_lastgeneric  ... last sweep always pipelined / always the generic 2-CTA/SM kernel
   direct_pf    ... with prefetch.global.L2 hints for the next tile's epilogue operands
   direct_nounroll ... flip-bit loop bounds taken at run time (no unrolling)
@@ -34,11 +35,13 @@ from dominantsparseeigenad_b200 import _lib  # noqa: E402
 from dominantsparseeigenad_b200.runtime import ptr, stream_ptr  # noqa: E402
 
 DEFAULTS = {"tfim_pipeline": 1, "tfim_tma": 1, "tfim_run_bits": 0, "tfim_direct": 1, "tfim_pipe_threads": 512,
-            "tfim_l2_prefetch": 0, "tfim_pipe_adjoint": 1, "tfim_unroll": 1, "tfim_generic_min_operands": 4}
+            "tfim_l2_prefetch": 0, "tfim_pipe_adjoint": 1, "tfim_unroll": 1, "tfim_generic_min_operands": 4,
+            "tfim_stage": 0}
 VARIANTS = {
     "r1_plan": {"tfim_run_bits": 2, "tfim_direct": 0, "tfim_unroll": 0},
     "sweeps3": {"tfim_direct": 0},
     "direct": {},
+    "staged": {"tfim_stage": 1},
     "direct_allpipe": {"tfim_generic_min_operands": 99},
     "direct_lastgeneric": {"tfim_generic_min_operands": 1},
     "direct_pf": {"tfim_l2_prefetch": 1},
