@@ -339,6 +339,7 @@ int dsea_ctx_set_option(dsea_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "basis_fp32")) ctx->basis_fp32 = (value != 0);
     else if (!strcmp(key, "fuse_small")) ctx->fuse_small = (value != 0);
     else if (!strcmp(key, "pdl")) ctx->pdl = (value != 0);
+    else if (!strcmp(key, "pdl_staged")) ctx->pdl_staged = (int)value;
     else if (!strcmp(key, "polish_eps_1e15")) ctx->polish_eps = 1e-15 * (double)(value < 1 ? 1 : value);
     else if (!strcmp(key, "p2p")) ctx->p2p_disabled = (value == 0);
     else if (!strcmp(key, "tfim_pipeline")) ctx->tfim_pipeline = (value != 0);

@@ -152,6 +152,7 @@ struct dsea_ctx {
     int reorth_ctas_per_sm = 8;         // persistent CTAs per SM for the reorth GEMVs (measured best of 2..8)
     double polish_eps = 1e-10;          // absolute CG tolerance of the Jacobi-Davidson polish (fp32 basis)
     int64_t last_polish_iters = 0;
+    int pdl_staged = 0;                 // experiment knob: bit 0 = staged sweep launched with the PDL attribute, bit 1 = it triggers its dependents early
     int pdl = 0;                        // programmatic dependent launch for every kernel (set to 1 by ctx_create when world == 1)
     int fuse_small = 1;                 // one GPU: consumers sum matvec / norm partials themselves (no finalize launches)
     int pending_dot_n = 0;              // > 0: the last matvec left this many dot partials at partials + kDotPartialsOffset
@@ -268,8 +269,8 @@ inline void count_launch(dsea_ctx* ctx, int n = 1) { ctx->launches += n; }
 // visible) BEFORE its first global-memory access.  That hides the 2-3 us launch latency between the ~2500 dependent
 // kernels of a solve without changing any ordering.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(const dsea_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                            cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_k_opt(const dsea_ctx* ctx, bool allow_pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                                size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -277,10 +278,15 @@ inline cudaError_t launch_k(const dsea_ctx* ctx, void (*kernel)(KArgs...), dim3 
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = (ctx && ctx->pdl) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (ctx && ctx->pdl && allow_pdl) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(const dsea_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, Args&&... args) {
+    return launch_k_opt(ctx, true, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 #endif
 
@@ -320,8 +326,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // running; a line the predecessor's CTAs load afterwards (the scalar block, a partial-sum array) can then survive in
 // that SM's L1 and be served, stale, to this grid after griddepcontrol.wait.  A gpu-scope fence compiles to
 // MEMBAR + CCTL.IVALL, which invalidates the SM's L1 after the wait, restoring the usual launch-boundary semantics.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+__device__ __forceinline__ void pdl_prologue(bool trigger = true) {
+    if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     __threadfence();
 }

@@ -67,6 +67,7 @@ struct SweepParams {
     int use_tma;            // 1: stage contiguous tiles with cp.async.bulk + mbarrier (pipelined kernel only)
     int l2_prefetch;        // 1: prefetch.global.L2 the next tile's epilogue operands
     int round_remote;       // 1: remote terms are fl32(remote_scale * y): the partner's fp32-rounded Lanczos vector
+    int pdl_trigger;        // staged kernel: 1 = let the next kernel's CTAs be scheduled while this one runs
 };
 
 // diag(s) = -(N - 2 popc(s ^ rotl_N(s))), an integer in [-N, N].  POPC and I2F run on the quarter-rate pipe (16 per clock
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
 // sub-tile.  Costs +1 LDS.128 per operand and pair (the flip phase stays well below the HBM time of the sweep).
 template <int MODE, int S, int LB>
 __global__ void __launch_bounds__(512, 1) tfim_sweep_staged_kernel(const SweepParams p) {
-    pdl_prologue();
+    pdl_prologue(p.pdl_trigger != 0);
     constexpr int T = kPipeT, THREADS = 512, PAIRS = 8, PPS = PAIRS / S, RBITS = 3, RB0 = T - RBITS;
     extern __shared__ __align__(128) double bufs[];            // 2 tiles of 2^13 doubles + the staging slots
     __shared__ double red[32];
@@ -668,7 +669,7 @@ static int launch_staged(dsea_ctx* ctx, const SweepParams& p, int grid, int nops
                                        (int)smem));
         set = smem;
     }
-    launch_k(ctx, tfim_sweep_staged_kernel<MODE, S, LB>, dim3(grid), dim3(512), smem, st, p);
+    launch_k_opt(ctx, (ctx->pdl_staged & 1) != 0, tfim_sweep_staged_kernel<MODE, S, LB>, dim3(grid), dim3(512), smem, st, p);
     count_launch(ctx);
     DSEA_CUDA(cudaGetLastError());
     return DSEA_OK;
@@ -794,6 +795,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         p.use_tma = (ctx->tfim_tma && sw[j].c == sw[j].T && (((uintptr_t)v) & 127u) == 0) ? 1 : 0;
         p.l2_prefetch = ctx->tfim_l2_prefetch;
         p.round_remote = (round_remote && p2p && prepushed) ? 1 : 0;
+        p.pdl_trigger = (ctx->pdl_staged & 2) ? 1 : 0;
         p.nrecv = last ? nrecv : 0;
         p.rank_off = (uint64_t)ctx->rank << L;
         p.n_loc = (uint64_t)op->n_loc;

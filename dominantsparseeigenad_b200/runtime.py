@@ -98,7 +98,7 @@ def context() -> Context:
                          ("mailbox", "DSEA_MAILBOX"), ("tfim_tma", "DSEA_TFIM_TMA"), ("basis_fp32", "DSEA_BASIS_FP32"),
                          ("tfim_direct", "DSEA_TFIM_DIRECT"), ("tfim_fuse_scale", "DSEA_TFIM_FUSE_SCALE"),
                          ("cg_fuse_push", "DSEA_CG_FUSE_PUSH"), ("tfim_pipe_threads", "DSEA_TFIM_PIPE_THREADS"),
-                         ("tfim_generic_min_operands", "DSEA_TFIM_GENERIC_MIN_OPERANDS"), ("pdl", "DSEA_PDL"),
+                         ("tfim_generic_min_operands", "DSEA_TFIM_GENERIC_MIN_OPERANDS"), ("pdl", "DSEA_PDL"), ("pdl_staged", "DSEA_PDL_STAGED"), ("tfim_stage", "DSEA_TFIM_STAGE"),
                          ("fuse_small", "DSEA_FUSE_SMALL")):
             if os.environ.get(env):
                 _ctx.set_option(key, int(os.environ[env]))
