@@ -120,8 +120,8 @@ def launches():
         agg[name][0] += 1
         agg[name][1] += num(r[col["Metric Value"]], unit)
     total = sum(v[1] for v in agg.values())
-    out = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 python bench.py --steps 1 --warmup 1 "
-                      "--no-cpu-baseline --no-extras   (warm-up solve + timed solve + e2e solves; cold-cache serialised times: "
+    out = {"command": "ncu --metrics gpu__time_duration.sum --clock-control none -c 2200 python bench.py --steps 1 --warmup 1 "
+                      "--no-cpu-baseline --no-extras   (the first 2200 launches = one complete solve and the start of the next; cold-cache serialised times: "
                       "compare SHARES)", "total_us": total,
            "kernels": {k: {"launches": v[0], "total_us": v[1], "share": v[1] / total}
                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}
