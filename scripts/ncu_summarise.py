@@ -130,7 +130,7 @@ def launches():
 
 
 if __name__ == "__main__":
-    recs = {tag: summarise_capture(tag) for tag in ("reorth_fp64", "reorth_fp32", "sweeps_L24", "sweeps_L26")}
+    recs = {tag: summarise_capture(tag) for tag in ("reorth_fp64", "reorth_fp32", "sweeps_L24", "sweeps_L26", "sweeps_adjoint_L24")}
     for tag, r in recs.items():
         for x in r or []:
             print(tag, x["kernel"][:60], "%.1f us" % x["duration_us"], "dram %.0f MB" % (x["dram_bytes"] / 1e6),
