@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
     const double scl = (MODE == MODE_FIRST && p.in_scale) ? *p.in_scale : 1.0;
     const double rscale = p.remote_scale ? *p.remote_scale : 1.0;
     const int bstart = LB > 0 ? LB : (p.b0 > 1 ? p.b0 : 1);
+    const bool fold_diag = (MODE == MODE_FIRST) && !p.no_diag && g != 0.0;
+    const double inv_g = fold_diag ? 1.0 / g : 0.0;
     double part = 0.0;
 
     auto eoff = [&](int j) -> uint32_t { return 2u * (threadIdx.x + THREADS * j); };   // tile offset of pair j
@@ -339,6 +341,18 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
                     }
                 }
             }
+            if (MODE == MODE_FIRST && fold_diag) {
+                // diagonal term folded into the accumulators while x is still in registers: its integer / popc /
+                // conversion work then runs in the shadow of the LDS phase instead of after it, and the epilogue
+                // shrinks to o = -g * scale * a.   u = (d - shift) x - g S  =  -g (S - ((d - shift) / g) x)
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    const uint64_t s = p.rank_off | gidx(base, eoff(j));
+                    const double d0 = tfim_diag_dev(s, p.N, nmask), d1 = tfim_diag_dev(s | 1ull, p.N, nmask);
+                    a[j].x -= ((d0 - shift) * inv_g) * x[j].x;
+                    a[j].y -= ((d1 - shift) * inv_g) * x[j].y;
+                }
+            }
         }                                                         // x is dead here: re-read from the tile when needed
         if (LB > 0) {
 #pragma unroll
@@ -393,17 +407,34 @@ __global__ void __launch_bounds__(THREADS, 1) tfim_sweep_pipe_kernel(const Sweep
         } else {
             const bool dot_self = p.w != nullptr && p.w == p.v;
             double2 o[PAIRS];
-            if (MODE == MODE_FIRST) {
+            if (MODE == MODE_FIRST && (fold_diag || p.no_diag)) {
+                const double mg = -g * scl;
+#pragma unroll
+                for (int j = 0; j < PAIRS; ++j) {
+                    o[j].x = mg * a[j].x;
+                    o[j].y = mg * a[j].y;
+                }
+                if (p.q_out || dot_self) {
+#pragma unroll
+                    for (int j = 0; j < PAIRS; ++j) {
+                        double2 x = *reinterpret_cast<const double2*>(buf + eoff(j));
+                        x.x *= scl;                               // the logical input (for q_out and the dot)
+                        x.y *= scl;
+                        if (p.q_out) stg2(p.q_out + gidx(base, eoff(j)), x);
+                        if (dot_self) part += x.x * o[j].x + x.y * o[j].y;
+                    }
+                }
+            } else if (MODE == MODE_FIRST) {                      // g == 0: u = (d - shift) x exactly
 #pragma unroll
                 for (int j = 0; j < PAIRS; ++j) {
                     double2 x = *reinterpret_cast<const double2*>(buf + eoff(j));
                     const uint64_t gi = gidx(base, eoff(j));
                     const uint64_t s = p.rank_off | gi;
-                    const double d0 = p.no_diag ? 0.0 : tfim_diag_dev(s, p.N, nmask);
-                    const double d1 = p.no_diag ? 0.0 : tfim_diag_dev(s | 1ull, p.N, nmask);
+                    const double d0 = tfim_diag_dev(s, p.N, nmask);
+                    const double d1 = tfim_diag_dev(s | 1ull, p.N, nmask);
                     o[j].x = scl * ((d0 - shift) * x.x - g * a[j].x);
                     o[j].y = scl * ((d1 - shift) * x.y - g * a[j].y);
-                    x.x *= scl;                                   // the logical input (for q_out and the dot)
+                    x.x *= scl;
                     x.y *= scl;
                     if (p.q_out) stg2(p.q_out + gi, x);
                     if (dot_self) part += x.x * o[j].x + x.y * o[j].y;
