@@ -857,7 +857,7 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         if (last && nrecv > 0 && !p2p) DSEA_CUDA(cudaStreamWaitEvent(st, ctx->ev_comm, 0));
         if (mode_adj) {
             p.w = w;
-            p.partials = ctx->partials + kDotPartialsOffset + total_partials;   // every sweep contributes partial sums
+            p.partials = ctx->partials + total_partials;   // every sweep contributes partial sums (main region: up to 40 sweeps x 2048)
             total_partials += grid;
             if (staged) DSEA_TRY(launch_staged_any<MODE_ADJ>(ctx, p, grid, nops, st));
             else DSEA_TRY(launch_sweep<MODE_ADJ>(ctx, p, grid, pipe, st));
@@ -877,7 +877,8 @@ static int tfim_run(dsea_ctx* ctx, const dsea_op* op, bool mode_adj, const doubl
         if (defer_dot && !mode_adj && ctx->world == 1 && ctx->fuse_small) {
             ctx->pending_dot_n = total_partials;      // the consumer kernel sums them in its prologue
         } else {
-            DSEA_TRY(finalize_reduce(ctx, total_partials, 1, dot_out, st, ctx->partials + kDotPartialsOffset));
+            DSEA_TRY(finalize_reduce(ctx, total_partials, 1, dot_out, st,
+                                     mode_adj ? ctx->partials : ctx->partials + kDotPartialsOffset));
         }
     }
     return DSEA_OK;
