@@ -330,7 +330,7 @@ static inline int reorth_grid(const dsea_ctx* ctx, int64_t n, int tile_rows, int
     const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
     int64_t cap = (int64_t)ctx->num_sms * ctx->reorth_ctas_per_sm;
     if (cap > kMaxPartialBlocks) cap = kMaxPartialBlocks;
-    if (cap * m > kPartialDoubles) cap = kPartialDoubles / m;
+    if (cap * m > kDotPartialsOffset) cap = kDotPartialsOffset / m;     // never reach into the matvec's dot-partials region
     if (cap < 1) cap = 1;
     return (int)(ntiles < cap ? ntiles : cap);
 }
