@@ -965,3 +965,23 @@ def test_zero_start_cg_matches_random_start(dsea):
     assert iters[0] == 0                                     # first backward: b = 0
     assert rel(E0, ex.E0) < EVAL_RTOL and rel(dE0, ex.dE0) < GRAD_RTOL and rel(d2E0, ex.d2E0) < GRAD_RTOL
     assert rel(chif, ex.chiF) < GRAD_RTOL
+
+
+def test_even_parity_start_vectors_cure_the_g_below_1_scatter(dsea):
+    """g = 0.5: the odd-parity partner of the ground state is only ~g^N above it, and with generic start vectors the
+    reference's own d2E0 / chi_F scatter by 1e-4 run to run.  With the opt-in even-sector start vectors the
+    second-order quantities meet the 1e-6 tolerance there as well, for different seeds."""
+    from dominantsparseeigenad_b200.analytic import tfim_exact
+    N, k, g = 16, 200, 0.5
+    ex = tfim_exact(N, g)
+    dsea.runtime.parity_sector = "even"
+    try:
+        for seed in (1, 2):
+            torch.manual_seed(seed)
+            E0, dE0, d2E0, psi = _tfim_E0_family(dsea, N, g, k)
+            chif = _tfim_chif(dsea, N, g, k)
+            assert rel(E0, ex.E0) < EVAL_RTOL and rel(dE0, ex.dE0) < GRAD_RTOL
+            assert rel(d2E0, ex.d2E0) < GRAD_RTOL and rel(chif, ex.chiF) < GRAD_RTOL, (seed, d2E0, ex.d2E0, chif, ex.chiF)
+            assert (psi - psi.flip(0)).abs().max().item() < 1e-9          # the eigenvector is even
+    finally:
+        dsea.runtime.parity_sector = "none"
