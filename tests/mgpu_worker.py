@@ -100,6 +100,22 @@ def main():
     dsea.runtime.set_basis_precision("fp64")
     assert rel(E32.item(), aE0) < 1e-10 and rel(dE32.item(), adE0) < 1e-6, (E32.item(), aE0, dE32.item(), adE0)
     assert 1 - abs(dsea.dot(psi32.detach(), psi0.detach()).item()) < 1e-8
+    # opt-in even-parity start vectors: the sharded spin flip pairs rank r with rank P-1-r
+    dsea.runtime.parity_sector = "even"
+    torch.manual_seed(5)
+    v_even = dsea.runtime.start_vector(m.n_loc, "lanczos")
+    assert (v_even - dsea.runtime.spin_flip(v_even)).abs().max().item() < 1e-12
+    mp = dsea.TFIM(N)
+    mp.g = torch.tensor([0.5], dtype=torch.float64, device=dev, requires_grad=True)
+    dsea.symeig.setDominantSparseSymeig(mp.H, mp.Hadjoint_to_gadjoint)
+    Ep, psip = dsea.symeig.DominantSparseSymeig.apply(mp.g, k, mp.dim, dev)
+    dEp, = torch.autograd.grad(Ep, mp.g, create_graph=True)
+    d2Ep, = torch.autograd.grad(dEp, mp.g)
+    dsea.runtime.parity_sector = "none"
+    pE0, pdE0, pd2E0, _ = orc.tfim_analytic(N, 0.5)
+    assert rel(Ep.item(), pE0) < 1e-10 and rel(dEp.item(), pdE0) < 1e-6 and rel(d2Ep.item(), pd2E0) < 1e-6, (d2Ep.item(), pd2E0)
+    assert (psip.detach() - dsea.runtime.spin_flip(psip.detach())).abs().max().item() < 1e-9
+    dsea.symeig.setDominantSparseSymeig(m.H, m.Hadjoint_to_gadjoint)
     # the oracle-free identities bench.py asserts in every multi-GPU run (each spin bit, remote ones included)
     from dominantsparseeigenad_b200 import selfcheck
     sc = selfcheck.run()
