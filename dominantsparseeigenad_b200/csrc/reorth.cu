@@ -91,6 +91,7 @@ struct RecT {
     double* r0_out;
     const double* alpha_partials;
     int n_alpha;
+    int skip_cols;      // 1 or 2: qi (and qim1) ARE the last columns of Q[:, :m]; their dots come from the prologue's registers
 };
 
 // ---- pass 1: partials[cta][j] = sum over the CTA's rows of Q[row, j] * u[row] -------------------
@@ -131,42 +132,70 @@ reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restri
             }
         }
         if (rec.qi) {
+            double di = 0.0, dm = 0.0;                               // q_i . r0 and q_{i-1} . r0 of this thread's rows
             if (full) {
-                double qa[R], qb[R];
+                double qa[R], qb[R], pa[R], pb[R];
                 TR::widen(TR::load(rec.qi + rA), qa);
                 TR::widen(TR::load(rec.qi + rB), qb);
 #pragma unroll
                 for (int e = 0; e < R; ++e) { ua[e] -= ra * qa[e]; ub[e] -= ra * qb[e]; }
                 if (rec.qim1) {
-                    TR::widen(TR::load(rec.qim1 + rA), qa);
-                    TR::widen(TR::load(rec.qim1 + rB), qb);
+                    TR::widen(TR::load(rec.qim1 + rA), pa);
+                    TR::widen(TR::load(rec.qim1 + rB), pb);
 #pragma unroll
-                    for (int e = 0; e < R; ++e) { ua[e] -= rb * qa[e]; ub[e] -= rb * qb[e]; }
+                    for (int e = 0; e < R; ++e) { ua[e] -= rb * pa[e]; ub[e] -= rb * pb[e]; }
                 }
 #pragma unroll
                 for (int e = 0; e < R; e += 2) {
                     stg2(rec.r0_out + rA + e, make_double2(ua[e], ua[e + 1]));
                     stg2(rec.r0_out + rB + e, make_double2(ub[e], ub[e + 1]));
                 }
+                if (rec.skip_cols > 0) {
+#pragma unroll
+                    for (int e = 0; e < R; ++e) di += qa[e] * ua[e];
+#pragma unroll
+                    for (int e = 0; e < R; ++e) di += qb[e] * ub[e];
+                    if (rec.skip_cols > 1) {
+#pragma unroll
+                        for (int e = 0; e < R; ++e) dm += pa[e] * ua[e];
+#pragma unroll
+                        for (int e = 0; e < R; ++e) dm += pb[e] * ub[e];
+                    }
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < R; ++e) {
                     if (rA + e < n) {
-                        ua[e] -= ra * (double)rec.qi[rA + e];
-                        if (rec.qim1) ua[e] -= rb * (double)rec.qim1[rA + e];
+                        const double qv = (double)rec.qi[rA + e], pv = rec.qim1 ? (double)rec.qim1[rA + e] : 0.0;
+                        ua[e] -= ra * qv;
+                        if (rec.qim1) ua[e] -= rb * pv;
                         rec.r0_out[rA + e] = ua[e];
+                        di += qv * ua[e];
+                        dm += pv * ua[e];
                     }
                     if (rB + e < n) {
-                        ub[e] -= ra * (double)rec.qi[rB + e];
-                        if (rec.qim1) ub[e] -= rb * (double)rec.qim1[rB + e];
+                        const double qv = (double)rec.qi[rB + e], pv = rec.qim1 ? (double)rec.qim1[rB + e] : 0.0;
+                        ub[e] -= ra * qv;
+                        if (rec.qim1) ub[e] -= rb * pv;
                         rec.r0_out[rB + e] = ub[e];
+                        di += qv * ub[e];
+                        dm += pv * ub[e];
                     }
                 }
             }
+            if (rec.skip_cols > 0) {                                  // columns m-1 (and m-2) are not streamed again below
+                di = warp_sum(di);
+                if (rec.skip_cols > 1) dm = warp_sum(dm);
+                if (lane == 0) {
+                    my[m - 1] += di;
+                    if (rec.skip_cols > 1) my[m - 2] += dm;
+                }
+            }
         }
-        for (int j0 = 0; j0 < m; j0 += kJB) {
+        const int mloop = m - rec.skip_cols;
+        for (int j0 = 0; j0 < mloop; j0 += kJB) {
             double acc[kJB];
-            if (full && j0 + kJB <= m) {
+            if (full && j0 + kJB <= mloop) {
                 typename TR::V a[kJB], b[kJB];
 #pragma unroll
                 for (int j = 0; j < kJB; ++j) {
@@ -190,7 +219,7 @@ reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restri
 #pragma unroll
                 for (int j = 0; j < kJB; ++j) {
                     acc[j] = 0.0;
-                    if (j0 + j < m) {
+                    if (j0 + j < mloop) {
                         const QT* col = Q + (int64_t)(j0 + j) * ldq;
 #pragma unroll
                         for (int e = 0; e < R; ++e) {
@@ -202,7 +231,7 @@ reorth_dots_kernel(const QT* __restrict__ Q, int64_t ldq, const double* __restri
             }
             const double tot = warp_reduce8(acc, lane);
             const int j = j0 + ((lane >> 2) & 7);
-            if ((lane & 3) == 0 && j < m) my[j] += tot;
+            if ((lane & 3) == 0 && j < mloop) my[j] += tot;
         }
     }
     __syncthreads();
@@ -347,14 +376,19 @@ static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT*
         smem_set = 200 * 1024;
     }
     const double s = (double)sizeof(QT);
-    const int tok = prof_begin(ctx, PK_REORTH_DOTS, (double)n * (s * m + 8.0 + (rec ? 2.0 * s + 8.0 : 0.0)), st);
     RecT<QT> rc;
     rc.qi = rc.qim1 = nullptr;
     rc.alpha = rc.beta = nullptr;
     rc.r0_out = nullptr;
     rc.alpha_partials = nullptr;
     rc.n_alpha = 0;
+    rc.skip_cols = 0;
     if (rec) {
+        // Lanczos: q_i and q_{i-1} are the last two stored columns; the prologue already holds them in registers
+        if (m >= 1 && rec->qi == (const void*)(Q + (int64_t)(m - 1) * ldq)) {
+            rc.skip_cols = 1;
+            if (m >= 2 && rec->qim1 == (const void*)(Q + (int64_t)(m - 2) * ldq)) rc.skip_cols = 2;
+        }
         rc.alpha_partials = rec->alpha_partials;
         rc.n_alpha = rec->n_alpha;
         rc.qi = (const QT*)rec->qi;
@@ -363,6 +397,10 @@ static int reorth_dots_t(dsea_ctx* ctx, int64_t n, int64_t ldq, int m, const QT*
         rc.beta = rec->beta;
         rc.r0_out = rec->r0_out;
     }
+    // bytes: u (8) + the m columns (s each; q_i / q_{i-1} are read ONCE, in the prologue) [+ r0 written (8) + recurrence
+    // operands that are not stored columns]
+    const int tok = prof_begin(ctx, PK_REORTH_DOTS,
+                               (double)n * (s * m + 8.0 + (rec ? 8.0 + s * (2 - rc.skip_cols) * (rc.qim1 ? 1.0 : 0.5) : 0.0)), st);
     launch_k(ctx, reorth_dots_kernel<QT>, dim3(grid), dim3(kRThreads), smem, st, Q, ldq, u, n, m, ctx->partials, rc);
     prof_end(ctx, tok, st);
     count_launch(ctx);

@@ -90,9 +90,9 @@ def traffic(recs_by_tag):
             if "reorth_update_kernel" in name:          # reads r0 (8) + m columns (s), writes r (8)
                 m = max(1, round((rd / N_LOC - 8) / s))
                 alg = N_LOC * (s * m + 16.0)
-            elif "reorth_dots_kernel" in name:          # reads u (8), q_i, q_{i-1} (s each) + m columns, writes r0 (8)
-                m = max(1, round((rd / N_LOC - 8 - 2 * s) / s))
-                alg = N_LOC * (s * m + 16.0 + 2 * s)
+            elif "reorth_dots_kernel" in name:          # reads u (8) + m columns (q_i, q_{i-1} among them, read once), writes r0 (8)
+                m = max(1, round((rd / N_LOC - 8) / s))
+                alg = N_LOC * (s * m + 16.0)
             else:
                 continue
             out.setdefault(name, []).append({"m": m, "dram_bytes": rec["dram_bytes"], "algorithmic_bytes": alg,
